@@ -1,0 +1,106 @@
+"""Pin the oracle: every committed golden vector of the reference's own specs for this path
+(SURVEY.md section 8c), whole-vector AND sample-by-sample (tests/jigs.lua:191-250), at the
+reference's epsilons."""
+import numpy as np
+import pytest
+
+from oracle import lr_oracle as O
+from tests.golden_util import all_block_specs, epsilon_ok, load_spec, GOLDEN_DIR
+from tests.oracle_blocks import make_oracle
+
+SPECS = [s for s in all_block_specs() if s != "multiplyconjugate_spec"]
+
+
+@pytest.mark.parametrize("spec", SPECS)
+def test_oracle_whole_vector(spec):
+    block, vectors, eps = load_spec(spec)
+    for v in vectors:
+        o = make_oracle(block, v["args"], v["inputs"])
+        got = o.process(v["inputs"][0])
+        ok, msg = epsilon_ok(got, v["outputs"][0], eps)
+        assert ok, "%s / %s: %s" % (block, v["desc"], msg)
+
+
+@pytest.mark.parametrize("spec", [s for s in SPECS if s not in ("tuner_spec", "decimator_spec")])
+def test_oracle_sample_by_sample(spec):
+    block, vectors, eps = load_spec(spec)
+    for v in vectors:
+        o = make_oracle(block, v["args"], v["inputs"])
+        x = v["inputs"][0]
+        outs = [o.process(x[i:i + 1]) for i in range(len(x))]
+        got = np.concatenate(outs) if outs else np.zeros(0, v["outputs"][0].dtype)
+        ok, msg = epsilon_ok(got, v["outputs"][0], eps)
+        assert ok, "%s / %s: %s" % (block, v["desc"], msg)
+
+
+def test_oracle_multiply_conjugate():
+    block, vectors, eps = load_spec("multiplyconjugate_spec")
+    for v in vectors:
+        ok, msg = epsilon_ok(O.multiply_conjugate(*v["inputs"]), v["outputs"][0], eps)
+        assert ok, msg
+
+
+def test_oracle_tap_design():
+    """tests/utilities/filter_utils_spec.lua:8-58 and window_utils_spec.lua at 1e-6."""
+    z = np.load(GOLDEN_DIR + "/filter_utils_vectors.npz")
+    cases = {
+        "firwin_lowpass": O.firwin_lowpass(128, 0.5),
+        "firwin_highpass": O.firwin_highpass(129, 0.5),
+        "firwin_bandpass": O.firwin_bandpass(129, [0.4, 0.6]),
+        "firwin_bandstop": O.firwin_bandstop(129, [0.4, 0.6]),
+        "firwin_complex_bandpass_positive": O.firwin_complex_bandpass(129, [0.1, 0.3]),
+        "firwin_complex_bandpass_negative": O.firwin_complex_bandpass(129, [-0.1, -0.3]),
+        "firwin_complex_bandpass_zero": O.firwin_complex_bandpass(129, [-0.2, 0.2]),
+        "firwin_complex_bandstop_positive": O.firwin_complex_bandstop(129, [0.1, 0.3]),
+        "firwin_complex_bandstop_negative": O.firwin_complex_bandstop(129, [-0.1, -0.3]),
+        "firwin_complex_bandstop_zero": O.firwin_complex_bandstop(129, [-0.2, 0.2]),
+        "fir_hilbert_transform": O.fir_hilbert_transform(129),
+    }
+    for k, h in cases.items():
+        ok, msg = epsilon_ok(O.f32_taps(h), z[k], 1e-6)
+        assert ok, "%s: %s" % (k, msg)
+    w = np.load(GOLDEN_DIR + "/window_utils_vectors.npz")
+    for name in ("rectangular", "hamming", "hanning", "bartlett", "blackman"):
+        for per in (False, True):
+            key = "window_" + name + ("_periodic" if per else "")
+            ok, msg = epsilon_ok(O.window(len(w[key]), name, per).astype(np.float32), w[key], 1e-6)
+            assert ok, "%s: %s" % (key, msg)
+
+
+def test_oracle_dft():
+    """tests/utilities/spectrum_utils_spec.lua:58-72 at 1e-5 (forward e^{-j}, inverse 1/N)."""
+    z = np.load(GOLDEN_DIR + "/spectrum_utils_vectors.npz")
+    ok, msg = epsilon_ok(O.dft(z["complex_test_vector"]), z["complex_test_vector_dft"], 1e-5)
+    assert ok, msg
+    ok, msg = epsilon_ok(O.dft(z["real_test_vector"]), z["real_test_vector_dft"], 1e-5)
+    assert ok, msg
+    ok, msg = epsilon_ok(O.idft(z["complex_test_vector_dft"]), z["complex_test_vector"], 1e-5)
+    assert ok, msg
+
+
+def test_oracle_top_chain():
+    """tests/top_spec.lua:14-55 against tests/top_vectors.py:6-24: MultiplyConjugate -> Lowpass(16, 100e3)
+    -> FrequencyDiscriminator(5) -> Decimator(25, num_taps=16) at rate 1e6, epsilon 1e-6."""
+    z = np.load(GOLDEN_DIR + "/top_vectors.npz")
+    x = O.multiply_conjugate(z["SRC1_TEST_VECTOR"], z["SRC2_TEST_VECTOR"])
+    x = O.lowpass_filter(16, 100e3, 1e6, True).process(x)
+    x = O.FrequencyDiscriminator(5.0).process(x)
+    x = O.decimator(25, False, num_taps=16).process(x)
+    ok, msg = epsilon_ok(x, z["SNK_TEST_VECTOR"], 1e-6)
+    assert ok, msg
+
+
+def test_oracle_chunking_invariance():
+    """Streaming state: ragged chunking must not change the WBFM-mono chain output."""
+    x = O.synth_fm_iq(0, 40000)
+    whole = O.wbfm_mono_chain().process(x)
+    c = O.wbfm_mono_chain()
+    rng = np.random.default_rng(3)
+    outs, i = [], 0
+    while i < len(x):
+        n = int(rng.integers(0, 3000))
+        outs.append(c.process(x[i:i + n]))
+        i += n
+    got = np.concatenate(outs)
+    assert got.shape == whole.shape
+    assert np.max(np.abs(got - whole)) < 1e-6
