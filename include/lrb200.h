@@ -1,0 +1,196 @@
+/*
+ * lrb200.h -- C ABI of libluaradio_b200.so: the B200 (sm_100a) implementation of LuaRadio's
+ * per-block sample-stream DSP hot path.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one FFI
+ * binding (or pure-Lua loop) of the reference, cited as `file:line` relative to the reference
+ * root (vsergeev/luaradio v0.11.0).  The conventions are the ones the reference's own FFI
+ * bindings use (liquid-dsp style, radio/blocks/signal/firfilter.lua:167-226):
+ *
+ *   - plain C: `extern "C"`, pointers and sizes only, no C++/torch types, no exceptions;
+ *   - sample types are binary-compatible with radio/types/complexfloat32.lua:19-24 and
+ *     radio/types/float32.lua:17-21 (interleaved I/Q float32 == CUDA float2; float32);
+ *   - stateful objects are an opaque handle with a  create / execute / reset / destroy  quartet;
+ *     create returns NULL on failure (the Lua wrapper raises error(), firfilter.lua:199-201);
+ *   - the CALLER owns every sample buffer; the library owns only its opaque state;
+ *   - execute consumes exactly n input samples (any n >= 0, including 1: tests/jigs.lua:226-243),
+ *     writes *n_out output samples and carries the block's streaming state (FIR history,
+ *     translator phase, discriminator previous sample, IIR state, downsampler index) to the
+ *     next call, exactly as the reference's process() does;
+ *   - execute returns 0 on success, <0 on failure with a message in lrb200_last_error();
+ *   - handles are not thread-safe (the reference runs one single-threaded process per block,
+ *     radio/core/composite.lua:568-636); different handles may be used from different threads.
+ *
+ * Pointer mode is fixed per handle at create time by `flags`:
+ *   LRB200_HOST    x / y are HOST pointers (pageable or pinned): drop-in mode, the call stages
+ *                  host->device, runs the kernels, copies device->host and synchronises.
+ *   LRB200_DEVICE  x / y are DEVICE pointers: the call only enqueues kernels on the library
+ *                  stream (lrb200_set_stream / lrb200_sync) -- graph mode, used when connected
+ *                  GPU blocks share device-resident buffers (lrb200_graph_*).
+ *
+ * There is NO CPU fallback anywhere in this library: without a CUDA device every create fails.
+ */
+#ifndef LRB200_H
+#define LRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* radio/types/complexfloat32.lua:19-24, radio/types/float32.lua:17-21 */
+typedef struct { float real; float imag; } complex_float32_t;
+typedef struct { float value; } float32_t;
+
+#define LRB200_HOST   0u
+#define LRB200_DEVICE 1u
+
+/* ---- library / device ---------------------------------------------------------------------
+ * Replaces the feature probe + ffi.load in radio/core/platform.lua:277-299 (platform.features.X,
+ * platform.libs.X).  lrb200_init is lazy-safe: create functions call it with the current device. */
+int         lrb200_init(int device);                 /* 0 ok, <0 error (no device, wrong arch)   */
+int         lrb200_device_count(void);               /* 0 when no CUDA device is usable          */
+const char* lrb200_last_error(void);                 /* thread-local, never NULL                 */
+const char* lrb200_version(void);
+int         lrb200_set_stream(void* cuda_stream);    /* use the caller's cudaStream_t (NULL = own) */
+void*       lrb200_get_stream(void);
+int         lrb200_sync(void);                       /* cudaStreamSynchronize on the library stream */
+uint64_t    lrb200_launch_count(void);               /* kernels launched by this library so far  */
+
+/* device / pinned memory for graph mode and source/sink boundaries (the reference's
+ * platform.alloc, radio/core/platform.lua:268-274, is the host analogue) */
+void* lrb200_malloc(size_t bytes);
+void  lrb200_free(void* dptr);
+void* lrb200_host_alloc(size_t bytes);               /* pinned */
+void  lrb200_host_free(void* hptr);
+int   lrb200_memcpy_h2d(void* dst, const void* src, size_t bytes);   /* async on the library stream */
+int   lrb200_memcpy_d2h(void* dst, const void* src, size_t bytes);   /* async on the library stream */
+int   lrb200_memset(void* dptr, int value, size_t bytes);
+
+/* ---- generic block handle ------------------------------------------------------------------
+ * Every block below is an lrb200_block_t; the typed names are aliases so the Lua cdef reads like
+ * the liquid bindings it sits beside.  lrb200_block_execute is what Block:process() calls
+ * (radio/core/block.lua:585). */
+typedef struct lrb200_block_s lrb200_block_t;
+
+int    lrb200_block_execute(lrb200_block_t* q, const void* x, size_t n, void* y, size_t* n_out);
+size_t lrb200_block_max_output(const lrb200_block_t* q, size_t n); /* upper bound on *n_out for n inputs */
+size_t lrb200_block_in_size(const lrb200_block_t* q);              /* bytes per input sample  */
+size_t lrb200_block_out_size(const lrb200_block_t* q);             /* bytes per output sample */
+int    lrb200_block_reset(lrb200_block_t* q);                      /* back to the state after create */
+int    lrb200_block_seek(lrb200_block_t* q, uint64_t sample_index); /* set the global input sample index
+                                                                       (translator phase, decimation phase)
+                                                                       for time-chunk sharding */
+void   lrb200_block_destroy(lrb200_block_t* q);
+const char* lrb200_block_name(const lrb200_block_t* q);
+
+/* ---- FIRFilterBlock (+ Lowpass/Highpass/Bandpass/Bandstop/ComplexBandpass/ComplexBandstop) ---
+ * Replaces: volk_32fc_32f_dot_prod_32fc / volk_32fc_x2_dot_prod_32fc / volk_32f_x2_dot_prod_32f
+ * called once per output sample (firfilter.lua:111-163), firfilt_{crcf,cccf,rrrf}_create /
+ * _execute_block (firfilter.lua:167-226), the pure-Lua loops (:244-305) and the FFTW/VOLK
+ * overlap-save path process_fft (:320-398).
+ *   y[n] = sum_{k<ntaps} taps[k] * x[n-k], zero initial history, history carried across calls.
+ * `taps` are in natural order (NOT reversed).  decim >= 1 fuses a DownsamplerBlock(decim)
+ * (downsampler.lua:40-56) behind the filter: only outputs at global input index == 0 mod decim
+ * are computed and written (this is what Tuner/Decimator need, composites/decimator.lua:34-41).
+ * Unlike process_fft the output is length-preserving with zero latency (n_out == n for decim 1),
+ * i.e. the dot-product semantics, whichever algorithm runs inside. */
+typedef lrb200_block_t lrb200_fir_t;
+lrb200_fir_t* lrb200_fir_create_crcf(const float32_t* taps, unsigned ntaps, unsigned decim, unsigned flags);         /* complex in, real taps    */
+lrb200_fir_t* lrb200_fir_create_cccf(const complex_float32_t* taps, unsigned ntaps, unsigned decim, unsigned flags); /* complex in, complex taps */
+lrb200_fir_t* lrb200_fir_create_rrrf(const float32_t* taps, unsigned ntaps, unsigned decim, unsigned flags);         /* real in, real taps       */
+int  lrb200_fir_execute(lrb200_fir_t* q, const void* x, size_t n, void* y, size_t* n_out);
+int  lrb200_fir_reset(lrb200_fir_t* q);
+void lrb200_fir_destroy(lrb200_fir_t* q);
+/* algorithm selection (FIRFilterBlock(taps, use_fft), firfilter.lua:43,55-62):
+ * 0 = automatic, 1 = force direct form, 2 = force fused overlap-save FFT */
+#define LRB200_FIR_AUTO   0
+#define LRB200_FIR_DIRECT 1
+#define LRB200_FIR_FFT    2
+int  lrb200_fir_set_algorithm(lrb200_fir_t* q, int algo);
+int  lrb200_fir_get_algorithm(const lrb200_fir_t* q);   /* the algorithm that will run (1 or 2) */
+
+/* ---- HilbertTransformBlock -------------------------------------------------------------------
+ * Replaces volk_32f_x2_dot_prod_32f / dotprod_rrrf_execute per sample (hilberttransform.lua:39-128)
+ * and the Lua loop (:132-167): out.real = x[n-(ntaps-1)/2], out.imag = sum_k taps[k] x[n-k].
+ * float32 in -> complex out; ntaps must be odd. */
+typedef lrb200_block_t lrb200_hilbert_t;
+lrb200_hilbert_t* lrb200_hilbert_create(const float32_t* taps, unsigned ntaps, unsigned flags);
+
+/* ---- FrequencyTranslatorBlock ---------------------------------------------------------------
+ * Replaces volk_32fc_s32fc_x2_rotator_32fc (frequencytranslator.lua:26-53), nco_crcf_mix_block_up
+ * (:55-89) and the Lua loop (:93-110): y[n] = x[n] * exp(j*omega*n_global).
+ * `turns_per_sample` = offset/rate (cycles per sample, any sign); the phase is the closed form of
+ * the global sample index in 64-bit fixed point, so it never drifts and any chunk can be
+ * processed independently (lrb200_block_seek). */
+typedef lrb200_block_t lrb200_rotator_t;
+lrb200_rotator_t* lrb200_rotator_create(double turns_per_sample, unsigned flags);
+
+/* ---- FrequencyDiscriminatorBlock -------------------------------------------------------------
+ * Replaces volk_32fc_x2_multiply_conjugate_32fc + volk_32fc_s32f_atan2_32f_a
+ * (frequencydiscriminator.lua:40-64) and the Lua loop (:68-88):
+ * y[n] = atan2(im, re of x[n]*conj(x[n-1])) / gain, gain = 2*pi*modulation_index; prev sample carried. */
+typedef lrb200_block_t lrb200_discrim_t;
+lrb200_discrim_t* lrb200_discrim_create(float gain, unsigned flags);
+
+/* ---- DownsamplerBlock -------------------------------------------------------------------------
+ * Replaces the LuaJIT gather loop (downsampler.lua:40-56): y[m] = x[index + m*factor], index carried.
+ * elem_size is 8 (complex) or 4 (float32). */
+typedef lrb200_block_t lrb200_downsample_t;
+lrb200_downsample_t* lrb200_downsample_create(unsigned factor, unsigned elem_size, unsigned flags);
+
+/* ---- IIRFilterBlock / SinglepoleLowpass / SinglepoleHighpass / FMDeemphasisFilterBlock --------
+ * Replaces iirfilt_{rrrf,crcf}_create/_execute_block (iirfilter.lua:63-109) and the Lua recurrence
+ * (:113-179): y[n] = (sum_j b[j] x[n-j] - sum_{j>=1} a[j] y[n-j]) / a[0], zero initial state.
+ * The recurrence is evaluated as a block-parallel affine scan with decoupled look-back (exact
+ * recurrence, not a truncated warm-up).  nb <= 9, na <= 9. */
+typedef lrb200_block_t lrb200_iir_t;
+lrb200_iir_t* lrb200_iir_create_rrrf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags);
+lrb200_iir_t* lrb200_iir_create_crcf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags);
+
+/* ---- ComplexMagnitudeBlock / ComplexToRealBlock -----------------------------------------------
+ * Replace the LuaJIT loops complexmagnitude.lua:28-36 (sqrt(re^2+im^2)) and complextoreal.lua:27-35. */
+lrb200_block_t* lrb200_cmag_create(unsigned flags);
+lrb200_block_t* lrb200_c2r_create(unsigned flags);
+
+/* ---- GPU flow graph: connected GPU blocks on one stream with device-resident buffers ----------
+ * Replaces, for a connected run of GPU blocks, the fork-per-block + socketpair plumbing of
+ * radio/core/composite.lua:568-636 and radio/core/pipe.lua:53-88,495-615: the chain
+ *   source -> b0 -> b1 -> ... -> sink
+ * runs in one process on one CUDA stream; intermediate sample vectors live in a device-resident
+ * ring of buffers and never touch the host; host<->device copies (pinned, cudaMemcpyAsync,
+ * double-buffered) happen only at the source and sink ends.  Adjacent blocks are fused into single
+ * kernels where the library has one (Translator->FIR->Downsampler == TunerBlock,
+ * FIR->Downsampler == DecimatorBlock, Discriminator->FIR, IIR->Downsampler).  Blocks added to a
+ * graph must have been created with LRB200_DEVICE and are owned by the graph afterwards. */
+typedef struct lrb200_graph_s lrb200_graph_t;
+lrb200_graph_t* lrb200_graph_create(void);
+int    lrb200_graph_append(lrb200_graph_t* g, lrb200_block_t* q);   /* connect q after the current tail */
+int    lrb200_graph_commit(lrb200_graph_t* g, int fuse);            /* fuse != 0: apply kernel fusion   */
+int    lrb200_graph_execute(lrb200_graph_t* g, const void* x, size_t n, void* y, size_t* n_out);        /* HOST in/out   */
+int    lrb200_graph_execute_device(lrb200_graph_t* g, const void* dx, size_t n, void* dy, size_t* n_out); /* DEVICE in/out, async */
+size_t lrb200_graph_max_output(const lrb200_graph_t* g, size_t n);
+int    lrb200_graph_reset(lrb200_graph_t* g);
+int    lrb200_graph_seek(lrb200_graph_t* g, uint64_t sample_index);
+int    lrb200_graph_num_stages(const lrb200_graph_t* g);            /* kernels stages after fusion */
+const char* lrb200_graph_describe(const lrb200_graph_t* g);         /* e.g. "tuner(128,/5) | discrim+fir(128) | iir1+down(/5)" */
+const char* lrb200_graph_stage_name(const lrb200_graph_t* g, int stage);
+/* per-stage device timing for roofline reporting: when enabled every execute brackets each stage with
+ * CUDA events on the library stream; lrb200_graph_stage_time_ms sums them (synchronises) and resets. */
+int    lrb200_graph_set_timing(lrb200_graph_t* g, int enable);
+double lrb200_graph_stage_time_ms(lrb200_graph_t* g, int stage, int* executions);
+void   lrb200_graph_destroy(lrb200_graph_t* g);
+
+/* ---- synthetic sources on the device (the reference analogues are
+ * radio/blocks/sources/{uniformrandom,signal}.lua) -- counter-based, so any window of the stream
+ * can be regenerated on any GPU.  dst is a DEVICE pointer; async on the library stream. */
+int lrb200_synth_white_iq(complex_float32_t* dst, uint64_t n0, size_t n, uint32_t seed);
+int lrb200_synth_fm_iq(complex_float32_t* dst, uint64_t n0, size_t n, uint32_t seed,
+                       double rate, double carrier, double deviation, float amp, float noise);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRB200_H */

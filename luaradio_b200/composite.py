@@ -1,0 +1,349 @@
+"""CompositeBlock: flow-graph construction and the single-process GPU scheduler.
+
+Graph building mirrors radio/core/composite.lua:111-216 (connect / aliasing), :302-424 (validate,
+differentiate in evaluation order, crawl hierarchical blocks down to concrete ports, connect pipes,
+validate rates, initialize).  Running differs by design (north_star): instead of fork-per-block over
+socketpairs (composite.lua:568-636) the graph runs in ONE process on ONE CUDA stream.  A linear run of
+GPU blocks between a source and a sink is handed to the library's flow graph (lrb200_graph_*), where
+the blocks share device-resident buffers and adjacent blocks are fused; host<->device copies happen
+only at the source and sink.  Non-linear graphs run block-by-block in evaluation order (the
+reference's run(false) round-robin, composite.lua:647-707), each block's process() still on the GPU.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .block import Block, Input, Output, Pipe, Port
+from .signal_blocks import (DownsamplerBlock, FMDeemphasisFilterBlock, FrequencyDiscriminatorBlock,
+                            FrequencyTranslatorBlock, GPUBlock, LowpassFilterBlock)
+from .types import ComplexFloat32, Float32, Vector
+
+
+# -------------------------------------------------------------------------------------------------
+# Minimal host-side sources/sinks for the boundary (the reference analogues are RawFileSource/Sink,
+# radio/blocks/sources/rawfile.lua:75-108, radio/blocks/sinks/rawfile.lua:60-67, on in-memory buffers)
+# -------------------------------------------------------------------------------------------------
+class ArraySource(Block):
+    name = "ArraySource"
+
+    def instantiate(self, array, rate, chunk=1 << 22):
+        a = np.ascontiguousarray(array)
+        self.data_type = ComplexFloat32 if np.iscomplexobj(a) else Float32
+        self.array = a.astype(self.data_type.dtype, copy=False)
+        self.rate = float(rate)
+        self.chunk = int(chunk)
+        self.pos = 0
+        self.add_type_signature([], [Output("out", self.data_type)])
+
+    def get_rate(self):
+        return self.rate
+
+    def process(self):
+        if self.pos >= len(self.array):
+            return None    # EOF (block.lua:588)
+        v = Vector.cast(self.array[self.pos:self.pos + self.chunk])
+        self.pos += v.length
+        return v
+
+
+class ArraySink(Block):
+    name = "ArraySink"
+
+    def instantiate(self):
+        self.chunks = []
+        self.add_type_signature([Input("in", lambda t: True)], [])
+
+    def process(self, x):
+        self.chunks.append(np.array(x.data, copy=True))
+
+    def result(self):
+        if not self.chunks:
+            return np.zeros(0, dtype=self.get_input_type().dtype if self.signature else np.float32)
+        return np.concatenate(self.chunks)
+
+
+# -------------------------------------------------------------------------------------------------
+def _evaluation_order(connections, blocks):
+    deps = {b: set() for b in blocks}
+    for inp, outp in connections.items():
+        if inp.aliased or outp.aliased:
+            continue
+        deps.setdefault(inp.owner, set()).add(outp.owner)
+        deps.setdefault(outp.owner, set())
+    order = []
+    while len(order) < len(deps):
+        progressed = False
+        for b, d in deps.items():
+            if b not in order and all(x in order for x in d):
+                order.append(b)
+                progressed = True
+                break
+        if not progressed:
+            raise AssertionError("Flow graph has a cycle.")
+    return order
+
+
+class CompositeBlock(Block):
+    name = "CompositeBlock"
+
+    def instantiate(self):
+        self._blocks = []
+        self._connections = {}      # input port (or aliased output) -> output port (or aliased input)
+        self._order = None
+        self._gpu_graph = None
+
+    def add_type_signature(self, inputs, outputs, *a):
+        Block.add_type_signature(self, inputs, outputs)
+        for p in self.inputs + self.outputs:
+            p.aliased = True
+
+    # -- composite.lua:111-131
+    def connect(self, *args):
+        if all(isinstance(a, Block) for a in args):
+            first = args[0]
+            for i, second in enumerate(args[1:], start=2):
+                assert len(first.outputs) == 1, 'Unexpected number of output ports in block %d "%s": found %d, expected 1.' % (i - 1, first.name, len(first.outputs))
+                assert len(second.inputs) == 1, 'Unexpected number of input ports in block %d "%s": found %d, expected 1.' % (i, second.name, len(second.inputs))
+                self._connect_by_name(first, first.outputs[0].name, second, second.inputs[0].name)
+                first = second
+        else:
+            self._connect_by_name(*args)
+        return self
+
+    # -- composite.lua:133-187
+    def _connect_by_name(self, src, src_port_name, dst, dst_port_name):
+        find = lambda blk, nm: next((p for p in (blk.outputs or []) + (blk.inputs or []) if p.name == nm), None)
+        src_port, dst_port = find(src, src_port_name), find(dst, dst_port_name)
+        assert src_port, 'Output port "%s" of block "%s" not found.' % (src_port_name, src.name)
+        assert dst_port, 'Input port "%s" of block "%s" not found.' % (dst_port_name, dst.name)
+        self._order = None
+        if src is not self and dst is not self:
+            assert src_port.kind == "out", "Source port %s.%s is not an output port." % (src.name, src_port.name)
+            assert dst_port.kind == "in", "Destination port %s.%s is not an input port." % (dst.name, dst_port.name)
+            assert dst_port not in self._connections, 'Input port "%s" of block "%s" already connected.' % (dst_port.name, dst.name)
+            self._connections[dst_port] = src_port
+            for b in (src, dst):
+                if b not in self._blocks:
+                    self._blocks.append(b)
+        else:
+            alias_port = src_port if src is self else dst_port
+            target_port = dst_port if src is self else src_port
+            if alias_port.kind == "in" and target_port.kind == "in":
+                assert target_port not in self._connections, "Input port %s.%s already connected." % (target_port.owner.name, target_port.name)
+                self._connections[target_port] = alias_port
+            elif alias_port.kind == "out" and target_port.kind == "out":
+                assert alias_port not in self._connections, "Output port %s.%s already connected." % (alias_port.owner.name, alias_port.name)
+                self._connections[alias_port] = target_port
+            else:
+                raise AssertionError("Malformed port connection.")
+            if target_port.owner not in self._blocks:
+                self._blocks.append(target_port.owner)
+
+    def _eval_order(self):
+        if self._order is None:
+            self._order = _evaluation_order(self._connections, self._blocks)
+        return self._order
+
+    # -- composite.lua:302-341
+    def _validate_inputs(self):
+        for b in self._blocks:
+            for p in b.inputs or []:
+                assert p in self._connections, 'Block "%s" input "%s" is unconnected.' % (b.name, p.name)
+            if isinstance(b, CompositeBlock):
+                b._validate_inputs()
+
+    def _differentiate(self):
+        for b in self._eval_order():
+            b.differentiate([self._connections[p].data_type for p in b.inputs])
+            if isinstance(b, CompositeBlock):
+                b._differentiate()
+        for out in self.outputs or []:
+            src = self._connections[out]
+            assert out.data_type is src.data_type, "Invalid type signature, composite output %s.%s data type does not match block output %s.%s." % (self.name, out.name, src.owner.name, src.name)
+
+    # -- composite.lua:343-379: flatten hierarchical blocks to concrete (input port -> output port)
+    def _crawl_connections(self, crawled=None, stack=()):
+        crawled = {} if crawled is None else crawled
+
+        def resolve(port):
+            if port.kind == "out" and not port.aliased:
+                return port
+            if port.kind == "out" and port.aliased:
+                return resolve(port.owner._connections[port])
+            for comp in stack:
+                if port in comp._connections:
+                    return resolve(comp._connections[port])
+            raise AssertionError("Unexpected disconnected composite input port %s.%s" % (port.owner.name, port.name))
+
+        for b in self._eval_order():
+            if isinstance(b, CompositeBlock):
+                b._crawl_connections(crawled, (self,) + tuple(stack))
+            else:
+                for p in b.inputs:
+                    crawled[p] = resolve(self._connections[p])
+        return crawled
+
+    def _prepare_to_run(self):
+        self._validate_inputs()
+        self._differentiate()
+        self._all_connections = self._crawl_connections()
+        for inp, outp in self._all_connections.items():
+            pipe = Pipe(outp, inp)
+            outp.pipes.append(pipe)
+            inp.pipe = pipe
+        concrete = []
+        for inp, outp in self._all_connections.items():
+            for b in (outp.owner, inp.owner):
+                if b not in concrete:
+                    concrete.append(b)
+        self._concrete_order = _evaluation_order(self._all_connections, concrete)
+        for b in self._concrete_order:           # rate validation, composite.lua:394-414
+            rates = [p.pipe.get_rate() for p in b.inputs]
+            assert all(r == rates[0] for r in rates), 'Block "%s" input sample rate mismatch.' % b.name
+        for b in self._concrete_order:           # composite.lua:416-424: initialize every block
+            b.initialize()
+
+    # ---------------------------------------------------------------------------------------------
+    def _linear_gpu_chain(self):
+        """[source, gpu blocks..., sink] if the flattened graph is one linear chain, else None."""
+        order = self._concrete_order
+        if len(order) < 3:
+            return None
+        for i, b in enumerate(order):
+            n_in, n_out = len(b.inputs), len(b.outputs)
+            if i == 0 and not (n_in == 0 and n_out == 1 and len(b.outputs[0].pipes) == 1):
+                return None
+            if 0 < i < len(order) - 1 and not (isinstance(b, GPUBlock) and n_in == 1 and n_out == 1 and len(b.outputs[0].pipes) == 1
+                                               and b.inputs[0].pipe.output.owner is order[i - 1]):
+                return None
+            if i == len(order) - 1 and not (n_in == 1 and n_out == 0 and b.inputs[0].pipe.output.owner is order[i - 1]):
+                return None
+        return order
+
+    def describe_gpu_graph(self):
+        return self._gpu_desc if getattr(self, "_gpu_desc", None) else ""
+
+    def run(self, multiprocess=False, fuse=True):
+        """Run to source EOF.  `multiprocess` is accepted for API compatibility; the GPU scheduler is
+        always single-process (a CUDA context does not survive fork())."""
+        self._prepare_to_run()
+        chain = self._linear_gpu_chain()
+        if chain is not None:
+            self._run_gpu_chain(chain, fuse)
+        else:
+            self._run_round_robin()
+        for b in self._concrete_order:
+            b.cleanup()
+        return self
+
+    def _run_gpu_chain(self, chain, fuse):
+        lib = _lib.require_device()
+        source, sink, blocks = chain[0], chain[-1], chain[1:-1]
+        g = _lib.check_handle(lib.lrb200_graph_create(), "lrb200 graph")
+        try:
+            for b in blocks:
+                h = b.make_device_handle()
+                _lib.check(lib.lrb200_graph_append(g, h), "graph_append(%s)" % b.name)
+            _lib.check(lib.lrb200_graph_commit(g, 1 if fuse else 0), "graph_commit")
+            self._gpu_desc = lib.lrb200_graph_describe(g).decode()
+            out_type = blocks[-1].get_output_type()
+            out = out_type.vector()
+            while True:
+                x = source.process()
+                if x is None:
+                    break
+                out.resize(lib.lrb200_graph_max_output(g, x.length))
+                n_out = ctypes.c_size_t(0)
+                _lib.check(lib.lrb200_graph_execute(g, x.ctypes_ptr(), x.length, out.ctypes_ptr(), ctypes.byref(n_out)), "graph_execute")
+                out.resize(n_out.value)
+                sink.process(out)
+        finally:
+            lib.lrb200_graph_destroy(g)
+
+    def _run_round_robin(self):
+        order = self._concrete_order
+        fifo = {}                      # input port -> list of numpy chunks
+        for inp in self._all_connections:
+            fifo[inp] = []
+        live = True
+        while live:
+            live = False
+            for b in order:
+                if not b.inputs:
+                    v = b.process()
+                    if v is None:
+                        continue
+                    outs = v if isinstance(v, tuple) else (v,)
+                    live = True
+                else:
+                    if any(len(fifo[p]) == 0 for p in b.inputs):
+                        continue
+                    arrays = [np.concatenate(fifo[p]) if len(fifo[p]) > 1 else fifo[p][0] for p in b.inputs]
+                    n = min(len(a) for a in arrays)
+                    if n == 0:
+                        continue
+                    for p, a in zip(b.inputs, arrays):
+                        fifo[p] = [a[n:]] if len(a) > n else []
+                    r = b.process(*[Vector.cast(a[:n]) for a in arrays])
+                    outs = () if r is None else (r if isinstance(r, tuple) else (r,))
+                    live = True
+                for port, vec in zip(b.outputs, outs):
+                    data = np.array(vec.data, copy=True)
+                    for pipe in port.pipes:
+                        fifo[pipe.input].append(data)
+
+
+# -------------------------------------------------------------------------------------------------
+# Composites on the hot path
+# -------------------------------------------------------------------------------------------------
+class TunerBlock(CompositeBlock):
+    """composites/tuner.lua:32-48: Translator(offset) -> Lowpass(num_taps or 128, bandwidth/2) -> Downsampler(D)."""
+    name = "TunerBlock"
+
+    def instantiate(self, offset, bandwidth, decimation, options=None):
+        CompositeBlock.instantiate(self)
+        assert offset is not None, "Missing argument #1 (offset)"
+        assert bandwidth is not None, "Missing argument #2 (bandwidth)"
+        assert decimation is not None, "Missing argument #3 (decimation)"
+        options = options or {}
+        translator = FrequencyTranslatorBlock(offset)
+        filt = LowpassFilterBlock(options.get("num_taps", 128), bandwidth / 2.0, None, options.get("window"))
+        downsampler = DownsamplerBlock(decimation)
+        self.connect(translator, filt, downsampler)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        self.connect(self, "in", translator, "in")
+        self.connect(self, "out", downsampler, "out")
+
+
+class DecimatorBlock(CompositeBlock):
+    """composites/decimator.lua:28-42: Lowpass(num_taps or 128, 1/D, nyquist 1.0) -> Downsampler(D)."""
+    name = "DecimatorBlock"
+
+    def instantiate(self, decimation, options=None):
+        CompositeBlock.instantiate(self)
+        assert decimation is not None, "Missing argument #1 (decimation)"
+        options = options or {}
+        filt = LowpassFilterBlock(options.get("num_taps", 128), 1.0 / decimation, 1.0, options.get("window"))
+        downsampler = DownsamplerBlock(decimation)
+        self.connect(filt, downsampler)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        self.add_type_signature([Input("in", Float32)], [Output("out", Float32)])
+        self.connect(self, "in", filt, "in")
+        self.connect(self, "out", downsampler, "out")
+
+
+class WBFMMonoDemodulator(CompositeBlock):
+    """composites/wbfmmonodemodulator.lua:22-35."""
+    name = "WBFMMonoDemodulator"
+
+    def instantiate(self, tau=None):
+        CompositeBlock.instantiate(self)
+        tau = tau or 75e-6
+        fm_demod = FrequencyDiscriminatorBlock(1.25)
+        af_filter = LowpassFilterBlock(128, 15e3)
+        af_deemphasis = FMDeemphasisFilterBlock(tau)
+        self.connect(fm_demod, af_filter, af_deemphasis)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
+        self.connect(self, "in", fm_demod, "in")
+        self.connect(self, "out", af_deemphasis, "out")

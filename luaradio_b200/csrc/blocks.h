@@ -1,0 +1,125 @@
+// Block objects behind the opaque C handles (internal).
+#pragma once
+#include "common.cuh"
+#include <vector>
+#include <string>
+
+namespace lrb {
+
+struct Block {
+    const char* name = "block";
+    size_t in_size = 8, out_size = 8;
+    bool dev_ptrs = false;
+    uint64_t consumed = 0;            // global index of the next input sample
+    void* d_in = nullptr;  size_t d_in_cap = 0;    // host-mode staging (grow-only, like Vector:resize)
+    void* d_out = nullptr; size_t d_out_cap = 0;
+
+    virtual ~Block();
+    virtual int init() { return 0; }
+    virtual size_t max_output(size_t n) const { return n; }
+    // device pointers in/out, asynchronous on s; consumes n, produces *n_out, advances the carried state
+    virtual int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) = 0;
+    virtual int reset() { consumed = 0; return 0; }
+    virtual int seek(uint64_t idx) { consumed = idx; return 0; }
+    // number of outputs this block has produced once `idx` inputs are consumed (for graph seek)
+    virtual uint64_t outputs_before(uint64_t idx) const { return idx; }
+    int execute(const void* x, size_t n, void* y, size_t* n_out);
+    static int reserve(void** p, size_t* cap, size_t bytes);
+};
+
+struct FirFast;   // overlap-save plan (fir_fft.cu)
+struct PolyTaps;  // polyphase decimator taps (tuner.cu)
+
+struct FirBlock : Block {
+    FirKind kind;
+    int M = 0, D = 1;
+    size_t tap_size = 4;
+    std::vector<char> h_taps;
+    void* d_taps = nullptr;
+    void* d_hist[2] = {nullptr, nullptr};
+    int cur = 0;
+    int algo = 0;                     // LRB200_FIR_AUTO / DIRECT / FFT
+    FirFast* fast = nullptr;
+    PolyTaps* poly = nullptr;
+
+    FirBlock(FirKind k, const void* taps_host, unsigned ntaps, unsigned decim, bool dev);
+    ~FirBlock() override;
+    int init() override;
+    size_t max_output(size_t n) const override;
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+    int reset() override;
+    uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+    // fast paths (fir_fft.cu): fast_run returns 1 if it handled the call, 0 to fall back, <0 on error
+    int fast_init();
+    void fast_free();
+    int fast_run(const void* dx, size_t n, void* dy, long long first, long long n_out, cudaStream_t s);
+    int set_algorithm(int a);
+    int effective_algorithm() const;
+};
+
+struct RotatorBlock : Block {
+    double turns = 0;
+    uint64_t turns_fix = 0;
+    RotatorBlock(double turns_per_sample, bool dev);
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
+struct DiscrimBlock : Block {
+    float gain = 1.f;
+    void* d_prev = nullptr;
+    DiscrimBlock(float gain, bool dev);
+    ~DiscrimBlock() override;
+    int init() override;
+    int reset() override;
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
+struct DownsampleBlock : Block {
+    int D = 1;
+    DownsampleBlock(unsigned factor, unsigned elem, bool dev);
+    size_t max_output(size_t n) const override;
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+    uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+};
+
+struct IirBlock : Block {
+    bool complex_data = false;
+    float b[9] = {0};
+    int nb = 1;
+    float c = 0.f;
+    int D = 1;                        // fused Downsampler behind the filter (graph fusion)
+    void* d_xhist[2] = {nullptr, nullptr};
+    void* d_ystate[2] = {nullptr, nullptr};
+    int cur = 0;
+    IirScanWork work;
+    IirBlock(bool cplx, const float* b, unsigned nb, const float* a, unsigned na, bool dev);
+    ~IirBlock() override;
+    int init() override;
+    size_t max_output(size_t n) const override;
+    int reset() override;
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+    uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+};
+
+struct C2fBlock : Block {
+    int op = 0;                       // 0 = magnitude, 1 = real part
+    C2fBlock(int op, bool dev);
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
+}  // namespace lrb
+
+// the opaque public handle
+struct lrb200_block_s { lrb::Block* impl; };
+
+namespace lrb {
+// tuner.cu: register-tiled polyphase decimating FIR (complex in, real taps), optional fused rotator.
+// Returns 1 if the (M, D) shape is supported and the launch was enqueued, 0 if unsupported, <0 on error.
+PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample);
+void polyphase_release(PolyTaps* p);
+int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist, long long n, float2* y,
+                          long long first, long long n_out, bool rotate, uint64_t turns_fix, uint64_t g0,
+                          cudaStream_t s);
+// tuner.cu: fused FrequencyTranslator -> FIR(crcf) -> Downsampler; returns nullptr (with the error set) on failure
+Block* make_tuner(double turns_per_sample, const float* taps, int ntaps, int decim);
+}  // namespace lrb

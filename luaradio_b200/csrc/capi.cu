@@ -1,0 +1,513 @@
+// C ABI of libluaradio_b200.so (include/lrb200.h): context, block objects with their carried
+// streaming state, and the single-stream GPU flow graph.  No CPU fallback: every entry point needs a
+// CUDA device and fails loudly (return code + lrb200_last_error) without one.
+#include "../../include/lrb200.h"
+#include "common.cuh"
+#include "blocks.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <new>
+
+namespace lrb {
+
+static thread_local char g_err[512] = "";
+static Ctx g_ctx;
+
+Ctx& ctx() { return g_ctx; }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+bool cuda_ok(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return false;
+}
+
+static int ensure_init() {
+    if (g_ctx.device >= 0) return 0;
+    return lrb200_init(0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block base: host-pointer (drop-in) mode stages through grow-only device buffers in chunks.
+// ---------------------------------------------------------------------------------------------
+static constexpr size_t HOST_CHUNK = (size_t)1 << 24;   // samples per staged chunk in host mode
+
+Block::~Block() {
+    cudaFree(d_in);
+    cudaFree(d_out);
+}
+
+int Block::reserve(void** p, size_t* cap, size_t bytes) {
+    if (bytes <= *cap) return 0;
+    cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    LRB_CHECK(cudaMalloc(p, bytes));
+    *cap = bytes;
+    return 0;
+}
+
+int Block::execute(const void* x, size_t n, void* y, size_t* n_out) {
+    cudaStream_t s = ctx().stream;
+    size_t produced = 0;
+    if (dev_ptrs) {
+        if (run(x, n, y, &produced, s) != 0) return -1;
+        if (n_out) *n_out = produced;
+        return 0;
+    }
+    size_t done = 0;
+    while (done < n) {
+        size_t nc = n - done < HOST_CHUNK ? n - done : HOST_CHUNK;
+        size_t mo = max_output(nc);
+        if (reserve(&d_in, &d_in_cap, nc * in_size) != 0) return -1;
+        if (reserve(&d_out, &d_out_cap, (mo ? mo : 1) * out_size) != 0) return -1;
+        LRB_CHECK(cudaMemcpyAsync(d_in, (const char*)x + done * in_size, nc * in_size, cudaMemcpyHostToDevice, s));
+        size_t no = 0;
+        if (run(d_in, nc, d_out, &no, s) != 0) return -1;
+        if (no) LRB_CHECK(cudaMemcpyAsync((char*)y + produced * out_size, d_out, no * out_size, cudaMemcpyDeviceToHost, s));
+        // the staging buffers are reused by the next chunk: drain before overwriting d_in
+        LRB_CHECK(cudaStreamSynchronize(s));
+        produced += no;
+        done += nc;
+    }
+    if (n_out) *n_out = produced;
+    return 0;
+}
+
+static inline void decim_plan(uint64_t consumed, unsigned D, size_t n, long long* first, long long* n_out) {
+    // downsampler.lua:45-53 in global-index form: outputs sit at global input index == 0 (mod D)
+    uint64_t r = consumed % D;
+    long long f = (long long)((D - r) % D);
+    *first = f;
+    *n_out = ((long long)n > f) ? (((long long)n - f + D - 1) / D) : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FIR (+ Hilbert)
+// ---------------------------------------------------------------------------------------------
+FirBlock::FirBlock(FirKind k, const void* taps_host, unsigned ntaps, unsigned decim, bool dev) {
+    kind = k;
+    M = (int)ntaps;
+    D = (int)decim;
+    dev_ptrs = dev;
+    const bool cin = (k == FIR_CRCF || k == FIR_CCCF);
+    in_size = cin ? 8 : 4;
+    out_size = (cin || k == FIR_HILBERT) ? 8 : 4;
+    tap_size = (k == FIR_CCCF) ? 8 : 4;
+    name = k == FIR_CRCF ? "fir_crcf" : k == FIR_CCCF ? "fir_cccf" : k == FIR_RRRF ? "fir_rrrf" : "hilbert";
+    h_taps.assign((const char*)taps_host, (const char*)taps_host + (size_t)M * tap_size);
+}
+
+int FirBlock::init() {
+    LRB_CHECK(cudaMalloc(&d_taps, (size_t)M * tap_size));
+    LRB_CHECK(cudaMemcpy(d_taps, h_taps.data(), (size_t)M * tap_size, cudaMemcpyHostToDevice));
+    size_t hb = (size_t)(M > 1 ? M - 1 : 1) * in_size;
+    for (int i = 0; i < 2; ++i) {
+        LRB_CHECK(cudaMalloc(&d_hist[i], hb));
+        LRB_CHECK(cudaMemset(d_hist[i], 0, hb));
+    }
+    return fast_init();
+}
+
+FirBlock::~FirBlock() {
+    cudaFree(d_taps);
+    cudaFree(d_hist[0]);
+    cudaFree(d_hist[1]);
+    fast_free();
+}
+
+size_t FirBlock::max_output(size_t n) const { return D == 1 ? n : n / D + 1; }
+
+int FirBlock::reset() {
+    consumed = 0;
+    cur = 0;
+    size_t hb = (size_t)(M > 1 ? M - 1 : 1) * in_size;
+    LRB_CHECK(cudaMemsetAsync(d_hist[0], 0, hb, ctx().stream));
+    LRB_CHECK(cudaMemsetAsync(d_hist[1], 0, hb, ctx().stream));
+    return 0;
+}
+
+int FirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    long long first, no;
+    decim_plan(consumed, (unsigned)D, n, &first, &no);
+    *n_out = (size_t)no;
+    if (n == 0) return 0;
+    int rc = fast_run(dx, n, dy, first, no, s);
+    if (rc < 0) return -1;
+    if (rc == 0) {
+        if (launch_fir_generic(kind, dx, d_hist[cur], d_taps, M, D, first, no, dy, s) != 0) return -1;
+    }
+    if (M > 1) {
+        if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, (int)in_size, s) != 0) return -1;
+        cur ^= 1;
+    }
+    consumed += n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FrequencyTranslator
+// ---------------------------------------------------------------------------------------------
+RotatorBlock::RotatorBlock(double turns_per_sample, bool dev) {
+    name = "rotator";
+    in_size = out_size = 8;
+    dev_ptrs = dev;
+    turns = turns_per_sample;
+    double t = turns_per_sample - std::floor(turns_per_sample);   // [0,1)
+    turns_fix = (uint64_t)std::ldexp(t, 64);
+}
+
+int RotatorBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    *n_out = n;
+    if (launch_rotator((const float2*)dx, (float2*)dy, (long long)n, turns_fix, consumed, s) != 0) return -1;
+    consumed += n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FrequencyDiscriminator
+// ---------------------------------------------------------------------------------------------
+DiscrimBlock::DiscrimBlock(float gain_, bool dev) {
+    name = "discrim";
+    in_size = 8;
+    out_size = 4;
+    dev_ptrs = dev;
+    gain = gain_;
+}
+int DiscrimBlock::init() {
+    LRB_CHECK(cudaMalloc(&d_prev, sizeof(float2)));
+    LRB_CHECK(cudaMemset(d_prev, 0, sizeof(float2)));
+    return 0;
+}
+DiscrimBlock::~DiscrimBlock() { cudaFree(d_prev); }
+int DiscrimBlock::reset() {
+    consumed = 0;
+    LRB_CHECK(cudaMemsetAsync(d_prev, 0, sizeof(float2), ctx().stream));
+    return 0;
+}
+int DiscrimBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    *n_out = n;
+    if (n == 0) return 0;
+    if (launch_discrim((const float2*)dx, (const float2*)d_prev, (float*)dy, (long long)n, 1.0f / gain, s) != 0) return -1;
+    if (launch_copy_last(dx, (long long)n, d_prev, 8, s) != 0) return -1;
+    consumed += n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Downsampler
+// ---------------------------------------------------------------------------------------------
+DownsampleBlock::DownsampleBlock(unsigned factor, unsigned elem, bool dev) {
+    name = "downsample";
+    in_size = out_size = elem;
+    dev_ptrs = dev;
+    D = (int)factor;
+}
+size_t DownsampleBlock::max_output(size_t n) const { return D == 1 ? n : n / D + 1; }
+int DownsampleBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    long long first, no;
+    decim_plan(consumed, (unsigned)D, n, &first, &no);
+    *n_out = (size_t)no;
+    if (launch_downsample(dx, dy, first, no, D, (int)in_size, s) != 0) return -1;
+    consumed += n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// IIR (single pole: na <= 2)
+// ---------------------------------------------------------------------------------------------
+IirBlock::IirBlock(bool cplx, const float* b_, unsigned nb_, const float* a_, unsigned na_, bool dev) {
+    name = cplx ? "iir_crcf" : "iir_rrrf";
+    in_size = out_size = cplx ? 8 : 4;
+    dev_ptrs = dev;
+    complex_data = cplx;
+    nb = (int)nb_;
+    double a0 = a_[0];
+    for (int j = 0; j < nb; ++j) b[j] = (float)((double)b_[j] / a0);
+    c = (na_ >= 2) ? (float)(-(double)a_[1] / a0) : 0.0f;
+}
+int IirBlock::init() {
+    size_t hb = (size_t)(nb > 1 ? nb - 1 : 1) * in_size;
+    for (int i = 0; i < 2; ++i) {
+        LRB_CHECK(cudaMalloc(&d_xhist[i], hb));
+        LRB_CHECK(cudaMemset(d_xhist[i], 0, hb));
+        LRB_CHECK(cudaMalloc(&d_ystate[i], in_size));
+        LRB_CHECK(cudaMemset(d_ystate[i], 0, in_size));
+    }
+    return iir_work_alloc(&work, (int)in_size);
+}
+IirBlock::~IirBlock() {
+    for (int i = 0; i < 2; ++i) { cudaFree(d_xhist[i]); cudaFree(d_ystate[i]); }
+    iir_work_free(&work);
+}
+size_t IirBlock::max_output(size_t n) const { return D == 1 ? n : n / D + 1; }
+int IirBlock::reset() {
+    consumed = 0;
+    cur = 0;
+    size_t hb = (size_t)(nb > 1 ? nb - 1 : 1) * in_size;
+    for (int i = 0; i < 2; ++i) {
+        LRB_CHECK(cudaMemsetAsync(d_xhist[i], 0, hb, ctx().stream));
+        LRB_CHECK(cudaMemsetAsync(d_ystate[i], 0, in_size, ctx().stream));
+    }
+    return 0;
+}
+int IirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    long long first_total, no_total;
+    decim_plan(consumed, (unsigned)D, n, &first_total, &no_total);
+    *n_out = (size_t)no_total;
+    const long long maxn = iir_max_per_launch(work);
+    size_t done = 0, produced = 0;
+    while (done < n) {
+        long long nc = (long long)(n - done) < maxn ? (long long)(n - done) : maxn;
+        long long first, no;
+        decim_plan(consumed, (unsigned)D, (size_t)nc, &first, &no);
+        if (launch_iir1(complex_data, (const char*)dx + done * in_size, nc, (char*)dy + produced * out_size, b, nb, c,
+                        d_xhist[cur], d_xhist[cur ^ 1], d_ystate[cur], d_ystate[cur ^ 1], first, D, &work, s) != 0)
+            return -1;
+        cur ^= 1;
+        consumed += (uint64_t)nc;
+        done += (size_t)nc;
+        produced += (size_t)no;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ComplexMagnitude / ComplexToReal
+// ---------------------------------------------------------------------------------------------
+C2fBlock::C2fBlock(int op_, bool dev) {
+    op = op_;
+    name = op == 0 ? "cmag" : "c2r";
+    in_size = 8;
+    out_size = 4;
+    dev_ptrs = dev;
+}
+int C2fBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    *n_out = n;
+    consumed += n;
+    return op == 0 ? launch_cmag((const float2*)dx, (float*)dy, (long long)n, s)
+                   : launch_c2r((const float2*)dx, (float*)dy, (long long)n, s);
+}
+
+}  // namespace lrb
+
+// =============================================================================================
+// extern "C" surface
+// =============================================================================================
+using namespace lrb;
+
+
+template <typename B>
+static lrb200_block_t* wrap(B* b) {
+    if (!b) { set_error("out of memory"); return nullptr; }
+    if (b->init() != 0) { delete b; return nullptr; }
+    lrb200_block_t* h = new (std::nothrow) lrb200_block_s{b};
+    if (!h) { delete b; set_error("out of memory"); }
+    return h;
+}
+
+extern "C" {
+
+int lrb200_init(int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("no CUDA device available (%s); libluaradio_b200 has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return -1;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return -1; }
+    LRB_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LRB_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return -1;
+    }
+    if (g_ctx.device != device) {
+        if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+        g_ctx.stream = nullptr;
+        g_ctx.own_stream = false;
+    }
+    g_ctx.device = device;
+    g_ctx.sm_count = prop.multiProcessorCount;
+    if (!g_ctx.stream) {
+        LRB_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        g_ctx.own_stream = true;
+    }
+    return 0;
+}
+
+int lrb200_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+const char* lrb200_last_error(void) { return g_err; }
+const char* lrb200_version(void) { return "luaradio_b200 0.1.0 (sm_100a)"; }
+
+int lrb200_set_stream(void* cuda_stream) {
+    if (ensure_init() != 0) return -1;
+    if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
+    g_ctx.own_stream = false;
+    g_ctx.stream = (cudaStream_t)cuda_stream;
+    if (!cuda_stream) {
+        LRB_CHECK(cudaStreamCreateWithFlags(&g_ctx.stream, cudaStreamNonBlocking));
+        g_ctx.own_stream = true;
+    }
+    return 0;
+}
+void* lrb200_get_stream(void) { return (void*)g_ctx.stream; }
+
+int lrb200_sync(void) {
+    if (ensure_init() != 0) return -1;
+    LRB_CHECK(cudaStreamSynchronize(g_ctx.stream));
+    return 0;
+}
+
+uint64_t lrb200_launch_count(void) { return g_ctx.launches.load(); }
+
+void* lrb200_malloc(size_t bytes) {
+    if (ensure_init() != 0) return nullptr;
+    void* p = nullptr;
+    if (!cuda_ok(cudaMalloc(&p, bytes ? bytes : 1), "cudaMalloc")) return nullptr;
+    return p;
+}
+void lrb200_free(void* p) { if (p) cudaFree(p); }
+void* lrb200_host_alloc(size_t bytes) {
+    if (ensure_init() != 0) return nullptr;
+    void* p = nullptr;
+    if (!cuda_ok(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault), "cudaHostAlloc")) return nullptr;
+    return p;
+}
+void lrb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+int lrb200_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+    if (ensure_init() != 0) return -1;
+    LRB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_ctx.stream));
+    return 0;
+}
+int lrb200_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+    if (ensure_init() != 0) return -1;
+    LRB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
+    return 0;
+}
+int lrb200_memset(void* p, int value, size_t bytes) {
+    if (ensure_init() != 0) return -1;
+    LRB_CHECK(cudaMemsetAsync(p, value, bytes, g_ctx.stream));
+    return 0;
+}
+
+// ---- generic block ---------------------------------------------------------------------------
+int lrb200_block_execute(lrb200_block_t* q, const void* x, size_t n, void* y, size_t* n_out) {
+    if (!q || !q->impl) { set_error("null block handle"); return -1; }
+    if (n > 0 && (!x || !y)) { set_error("%s: null sample buffer", q->impl->name); return -1; }
+    return q->impl->execute(x, n, y, n_out);
+}
+size_t lrb200_block_max_output(const lrb200_block_t* q, size_t n) { return q && q->impl ? q->impl->max_output(n) : 0; }
+size_t lrb200_block_in_size(const lrb200_block_t* q) { return q && q->impl ? q->impl->in_size : 0; }
+size_t lrb200_block_out_size(const lrb200_block_t* q) { return q && q->impl ? q->impl->out_size : 0; }
+int lrb200_block_reset(lrb200_block_t* q) {
+    if (!q || !q->impl) { set_error("null block handle"); return -1; }
+    return q->impl->reset();
+}
+int lrb200_block_seek(lrb200_block_t* q, uint64_t idx) {
+    if (!q || !q->impl) { set_error("null block handle"); return -1; }
+    return q->impl->seek(idx);
+}
+void lrb200_block_destroy(lrb200_block_t* q) {
+    if (!q) return;
+    delete q->impl;
+    delete q;
+}
+const char* lrb200_block_name(const lrb200_block_t* q) { return q && q->impl ? q->impl->name : ""; }
+
+// ---- FIR ---------------------------------------------------------------------------------------
+static lrb200_block_t* fir_create(FirKind k, const void* taps, unsigned ntaps, unsigned decim, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (!taps || ntaps == 0) { set_error("fir: taps must be non-empty"); return nullptr; }
+    if (decim == 0) { set_error("fir: decimation must be >= 1"); return nullptr; }
+    if (k == FIR_HILBERT && (ntaps % 2) == 0) { set_error("hilbert: number of taps must be odd"); return nullptr; }
+    return wrap(new (std::nothrow) FirBlock(k, taps, ntaps, decim, (flags & LRB200_DEVICE) != 0));
+}
+lrb200_fir_t* lrb200_fir_create_crcf(const float32_t* taps, unsigned ntaps, unsigned decim, unsigned flags) { return fir_create(FIR_CRCF, taps, ntaps, decim, flags); }
+lrb200_fir_t* lrb200_fir_create_cccf(const complex_float32_t* taps, unsigned ntaps, unsigned decim, unsigned flags) { return fir_create(FIR_CCCF, taps, ntaps, decim, flags); }
+lrb200_fir_t* lrb200_fir_create_rrrf(const float32_t* taps, unsigned ntaps, unsigned decim, unsigned flags) { return fir_create(FIR_RRRF, taps, ntaps, decim, flags); }
+int lrb200_fir_execute(lrb200_fir_t* q, const void* x, size_t n, void* y, size_t* n_out) { return lrb200_block_execute(q, x, n, y, n_out); }
+int lrb200_fir_reset(lrb200_fir_t* q) { return lrb200_block_reset(q); }
+void lrb200_fir_destroy(lrb200_fir_t* q) { lrb200_block_destroy(q); }
+int lrb200_fir_set_algorithm(lrb200_fir_t* q, int algo) {
+    FirBlock* f = q && q->impl ? dynamic_cast<FirBlock*>(q->impl) : nullptr;
+    if (!f) { set_error("not a FIR handle"); return -1; }
+    return f->set_algorithm(algo);
+}
+int lrb200_fir_get_algorithm(const lrb200_fir_t* q) {
+    FirBlock* f = q && q->impl ? dynamic_cast<FirBlock*>(q->impl) : nullptr;
+    if (!f) { set_error("not a FIR handle"); return -1; }
+    return f->effective_algorithm();
+}
+
+lrb200_hilbert_t* lrb200_hilbert_create(const float32_t* taps, unsigned ntaps, unsigned flags) { return fir_create(FIR_HILBERT, taps, ntaps, 1, flags); }
+
+lrb200_rotator_t* lrb200_rotator_create(double turns_per_sample, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (!std::isfinite(turns_per_sample)) { set_error("rotator: turns_per_sample is not finite"); return nullptr; }
+    return wrap(new (std::nothrow) RotatorBlock(turns_per_sample, (flags & LRB200_DEVICE) != 0));
+}
+
+lrb200_discrim_t* lrb200_discrim_create(float gain, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (!(gain != 0.0f) || !std::isfinite(gain)) { set_error("discrim: gain must be finite and non-zero"); return nullptr; }
+    return wrap(new (std::nothrow) DiscrimBlock(gain, (flags & LRB200_DEVICE) != 0));
+}
+
+lrb200_downsample_t* lrb200_downsample_create(unsigned factor, unsigned elem_size, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (factor == 0) { set_error("downsample: factor must be >= 1"); return nullptr; }
+    if (elem_size != 4 && elem_size != 8) { set_error("downsample: elem_size must be 4 or 8"); return nullptr; }
+    return wrap(new (std::nothrow) DownsampleBlock(factor, elem_size, (flags & LRB200_DEVICE) != 0));
+}
+
+static lrb200_block_t* iir_create(bool cplx, const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (!b || nb == 0 || !a || na == 0) { set_error("iir: b and a taps must be non-empty"); return nullptr; }
+    if (nb > 9) { set_error("iir: at most 9 feed-forward taps"); return nullptr; }
+    if (na > 2) { set_error("iir: only single-pole (na <= 2) recurrences are implemented on the GPU in this build"); return nullptr; }
+    if (a[0].value == 0.0f) { set_error("iir: a[0] must be non-zero"); return nullptr; }
+    return wrap(new (std::nothrow) IirBlock(cplx, (const float*)b, nb, (const float*)a, na, (flags & LRB200_DEVICE) != 0));
+}
+lrb200_iir_t* lrb200_iir_create_rrrf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags) { return iir_create(false, b, nb, a, na, flags); }
+lrb200_iir_t* lrb200_iir_create_crcf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags) { return iir_create(true, b, nb, a, na, flags); }
+
+lrb200_block_t* lrb200_cmag_create(unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    return wrap(new (std::nothrow) C2fBlock(0, (flags & LRB200_DEVICE) != 0));
+}
+lrb200_block_t* lrb200_c2r_create(unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    return wrap(new (std::nothrow) C2fBlock(1, (flags & LRB200_DEVICE) != 0));
+}
+
+// ---- synthetic sources -------------------------------------------------------------------------
+int lrb200_synth_white_iq(complex_float32_t* dst, uint64_t n0, size_t n, uint32_t seed) {
+    if (ensure_init() != 0) return -1;
+    return launch_synth_white((float2*)dst, n0, (long long)n, seed, g_ctx.stream);
+}
+int lrb200_synth_fm_iq(complex_float32_t* dst, uint64_t n0, size_t n, uint32_t seed, double rate, double carrier,
+                       double deviation, float amp, float noise) {
+    if (ensure_init() != 0) return -1;
+    return launch_synth_fm((float2*)dst, n0, (long long)n, seed, rate, carrier, deviation, amp, noise, g_ctx.stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,91 @@
+// Internal declarations shared by the kernels and the C ABI (not installed; the public surface is
+// include/lrb200.h).  All launchers are asynchronous on the given stream.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <atomic>
+
+namespace lrb {
+
+struct Ctx {
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::atomic<uint64_t> launches{0};
+};
+Ctx& ctx();
+void set_error(const char* fmt, ...);
+bool cuda_ok(cudaError_t e, const char* what);
+
+#define LRB_CHECK(call)                                   \
+    do {                                                  \
+        if (!::lrb::cuda_ok((call), #call)) return -1;    \
+    } while (0)
+
+inline void count_launch(int n = 1) { ctx().launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+enum FirKind { FIR_CRCF = 0, FIR_CCCF = 1, FIR_RRRF = 2, FIR_HILBERT = 3 };
+
+// ---- fir_direct.cu ----------------------------------------------------------------------------
+// Generic direct form: any ntaps, any decimation.  Logical input index i in [-(M-1), n): i < 0
+// reads hist[M-1+i].  Output j (0 <= j < n_out) is the filter output at input index first + j*D.
+int launch_fir_generic(FirKind kind, const void* x, const void* hist, const void* taps, int M, int D,
+                       long long first, long long n_out, void* y, cudaStream_t s);
+// new_hist[j] = logical(n - H + j), j in [0,H), over the concatenation [old_hist | x].
+int launch_hist_update(const void* x, long long n, const void* hist_old, void* hist_new, int H,
+                       int elem_size, cudaStream_t s);
+
+// ---- elementwise.cu ---------------------------------------------------------------------------
+int launch_rotator(const float2* x, float2* y, long long n, uint64_t turns_fix, uint64_t g0, cudaStream_t s);
+int launch_discrim(const float2* x, const float2* prev, float* y, long long n, float inv_gain, cudaStream_t s);
+int launch_downsample(const void* x, void* y, long long first, long long n_out, int D, int elem_size, cudaStream_t s);
+int launch_cmag(const float2* x, float* y, long long n, cudaStream_t s);
+int launch_c2r(const float2* x, float* y, long long n, cudaStream_t s);
+int launch_copy_last(const void* x, long long n, void* dst, int elem_size, cudaStream_t s);
+
+// ---- iir.cu -----------------------------------------------------------------------------------
+// y[n] = sum_{j<nb} b[j] x[n-j] + c*y[n-1]   (c = -a1/a0, b already divided by a0)
+// xhist: nb-1 previous inputs (oldest first), ystate: previous output.  State buffers are
+// ping-ponged by the caller: *_in is read, *_out written.  Fused decimation: only outputs whose
+// index (first + j*D) are written when D > 1.
+struct IirScanWork {           // device-side scratch for the decoupled look-back
+    int* ticket = nullptr;     // 1 int
+    int* flags = nullptr;      // max_tiles ints
+    void* agg = nullptr;       // max_tiles elements
+    void* pfx = nullptr;       // max_tiles elements
+    int max_tiles = 0;
+    unsigned epoch = 0;
+};
+int iir_work_alloc(IirScanWork* w, int elem_size);
+void iir_work_free(IirScanWork* w);
+long long iir_max_per_launch(const IirScanWork& w);
+int launch_iir1(bool complex_data, const void* x, long long n, void* y, const float* b_host, int nb, float c,
+                const void* xhist_in, void* xhist_out, const void* ystate_in, void* ystate_out,
+                long long first, int D, IirScanWork* w, cudaStream_t s);
+
+// ---- synth.cu ---------------------------------------------------------------------------------
+int launch_synth_white(float2* dst, uint64_t n0, long long n, uint32_t seed, cudaStream_t s);
+int launch_synth_fm(float2* dst, uint64_t n0, long long n, uint32_t seed, double rate, double carrier,
+                    double deviation, float amp, float noise, cudaStream_t s);
+
+// ---- device helpers ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+// exp(j*2*pi*turns) for turns given as a 64-bit fixed-point fraction of a cycle.
+__device__ __forceinline__ float2 phasor_from_fix(uint64_t ph) {
+    // top 32 bits as a signed fraction of a half-turn: t in [-1, 1)
+    int t = (int)(uint32_t)(ph >> 32);
+    float half_turns = (float)t * 4.656612873077393e-10f;  // 2^-31
+    float s, c;
+    sincospif(half_turns, &s, &c);
+    return make_float2(c, s);
+}
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    // (a.x + j a.y)(b.x + j b.y): FMUL2 + FFMA2 with the .LO_HI.NP operand swizzle on sm_100
+    float2 t = __fmul2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y));
+    return __ffma2_rn(a, make_float2(b.x, b.x), t);
+}
+#endif
+
+}  // namespace lrb

@@ -1,0 +1,341 @@
+// Single-stream GPU flow graph: a connected chain of GPU blocks sharing device-resident buffers.
+//
+// Replaces, for a run of connected GPU blocks, the reference's fork-per-block scheduler and socketpair
+// pipes (radio/core/composite.lua:568-636, radio/core/pipe.lua:53-88): intermediate sample vectors stay
+// in a two-slot device ring; host<->device traffic exists only at the two ends, double-buffered on
+// separate copy streams so chunk i+1 uploads while chunk i computes and chunk i-1 downloads.
+// commit(fuse=1) rewrites adjacent blocks into fused kernels:
+//   Rotator -> FIR(crcf) -> Downsampler   =>  tuner kernel      (composites/tuner.lua:40-47)
+//   FIR -> Downsampler                    =>  decimating FIR    (composites/decimator.lua:34-41)
+//   IIR -> Downsampler                    =>  scan with strided store
+#include "../../include/lrb200.h"
+#include "common.cuh"
+#include "blocks.h"
+
+#include <new>
+#include <string>
+#include <vector>
+
+namespace lrb {
+
+struct Graph {
+    std::vector<Block*> blocks;      // as appended (owned)
+    std::vector<Block*> fused;       // blocks created by fusion (owned)
+    std::vector<Block*> stages;      // execution order after commit (not owned)
+    bool committed = false;
+    void* ring[2] = {nullptr, nullptr};
+    size_t ring_cap[2] = {0, 0};
+    // host-mode double buffering
+    void* d_in[2] = {nullptr, nullptr};  size_t d_in_cap[2] = {0, 0};
+    void* d_out[2] = {nullptr, nullptr}; size_t d_out_cap[2] = {0, 0};
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    size_t host_chunk = (size_t)1 << 23;   // input samples per pipelined chunk
+    std::string desc;
+    // optional per-stage timing
+    bool timing = false;
+    std::vector<std::vector<cudaEvent_t>> tev;   // per stage: [start0, stop0, start1, stop1, ...]
+    std::vector<int> tcount;
+
+    cudaEvent_t timing_event(size_t stage, size_t idx) {
+        if (tev.size() < stages.size()) { tev.resize(stages.size()); tcount.assign(stages.size(), 0); }
+        auto& v = tev[stage];
+        while (v.size() <= idx) { cudaEvent_t e; cudaEventCreate(&e); v.push_back(e); }
+        return v[idx];
+    }
+
+    ~Graph() {
+        for (auto& v : tev) for (cudaEvent_t e : v) cudaEventDestroy(e);
+        for (Block* b : blocks) delete b;
+        for (Block* b : fused) delete b;
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(ring[i]); cudaFree(d_in[i]); cudaFree(d_out[i]);
+            if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+            if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+        }
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+    }
+
+    size_t max_output(size_t n) const {
+        for (Block* b : stages) n = b->max_output(n);
+        return n;
+    }
+
+    int commit(int fuse) {
+        stages.clear();
+        for (Block* b : fused) delete b;
+        fused.clear();
+        desc.clear();
+        size_t i = 0;
+        while (i < blocks.size()) {
+            Block* b = blocks[i];
+            Block* st = b;
+            size_t used = 1;
+            if (fuse) {
+                RotatorBlock* rot = dynamic_cast<RotatorBlock*>(b);
+                FirBlock* fir = dynamic_cast<FirBlock*>(b);
+                IirBlock* iir = dynamic_cast<IirBlock*>(b);
+                if (rot && i + 2 < blocks.size()) {
+                    FirBlock* f2 = dynamic_cast<FirBlock*>(blocks[i + 1]);
+                    DownsampleBlock* d3 = dynamic_cast<DownsampleBlock*>(blocks[i + 2]);
+                    if (f2 && d3 && f2->kind == FIR_CRCF && f2->D == 1 && d3->in_size == 8) {
+                        Block* t = make_tuner(rot->turns, (const float*)f2->h_taps.data(), f2->M, d3->D);
+                        if (t) { fused.push_back(t); st = t; used = 3; }
+                    }
+                }
+                if (used == 1 && fir && fir->D == 1 && fir->kind != FIR_HILBERT && i + 1 < blocks.size()) {
+                    DownsampleBlock* d2 = dynamic_cast<DownsampleBlock*>(blocks[i + 1]);
+                    if (d2 && d2->in_size == fir->out_size) {
+                        FirBlock* nf = new (std::nothrow) FirBlock(fir->kind, fir->h_taps.data(), (unsigned)fir->M, (unsigned)d2->D, true);
+                        if (!nf || nf->init() != 0) { delete nf; return -1; }
+                        fused.push_back(nf); st = nf; used = 2;
+                    }
+                }
+                if (used == 1 && iir && iir->D == 1 && i + 1 < blocks.size()) {
+                    DownsampleBlock* d2 = dynamic_cast<DownsampleBlock*>(blocks[i + 1]);
+                    if (d2 && d2->in_size == iir->out_size) {
+                        float a[2] = {1.0f, -iir->c};
+                        IirBlock* ni = new (std::nothrow) IirBlock(iir->complex_data, iir->b, (unsigned)iir->nb, a, 2, true);
+                        if (!ni) { set_error("out of memory"); return -1; }
+                        ni->D = d2->D;
+                        if (ni->init() != 0) { delete ni; return -1; }
+                        fused.push_back(ni); st = ni; used = 2;
+                    }
+                }
+            }
+            stages.push_back(st);
+            if (!desc.empty()) desc += " | ";
+            desc += st->name;
+            if (used > 1) { desc += "[fused x"; desc += std::to_string(used); desc += "]"; }
+            i += used;
+        }
+        for (size_t k = 0; k + 1 < stages.size(); ++k) {
+            if (stages[k]->out_size != stages[k + 1]->in_size) {
+                set_error("graph: %s (out %zu B) cannot feed %s (in %zu B)", stages[k]->name, stages[k]->out_size,
+                          stages[k + 1]->name, stages[k + 1]->in_size);
+                return -1;
+            }
+        }
+        committed = true;
+        return 0;
+    }
+
+    // device in/out, asynchronous on s
+    int run_device(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+        if (!committed && commit(1) != 0) return -1;
+        if (stages.empty()) { set_error("graph: no blocks"); return -1; }
+        // size the ring for this n
+        size_t m = n;
+        for (size_t k = 0; k + 1 < stages.size(); ++k) {
+            m = stages[k]->max_output(m);
+            size_t bytes = (m ? m : 1) * stages[k]->out_size;
+            int slot = (int)(k & 1);
+            if (bytes > ring_cap[slot]) {
+                // a stage still in flight may be reading the old buffer
+                LRB_CHECK(cudaStreamSynchronize(s));
+                if (Block::reserve(&ring[slot], &ring_cap[slot], bytes) != 0) return -1;
+            }
+        }
+        const void* in = dx;
+        size_t cnt = n;
+        for (size_t k = 0; k < stages.size(); ++k) {
+            void* out = (k + 1 == stages.size()) ? dy : ring[k & 1];
+            size_t no = 0;
+            if (timing) {
+                if (tcount.size() < stages.size()) { tev.resize(stages.size()); tcount.assign(stages.size(), 0); }
+                cudaEventRecord(timing_event(k, 2 * (size_t)tcount[k]), s);
+            }
+            if (stages[k]->run(in, cnt, out, &no, s) != 0) return -1;
+            if (timing) { cudaEventRecord(timing_event(k, 2 * (size_t)tcount[k] + 1), s); tcount[k]++; }
+            in = out;
+            cnt = no;
+        }
+        *n_out = cnt;
+        return 0;
+    }
+
+    int ensure_host_pipeline() {
+        if (s_h2d) return 0;
+        LRB_CHECK(cudaStreamCreateWithFlags(&s_h2d, cudaStreamNonBlocking));
+        LRB_CHECK(cudaStreamCreateWithFlags(&s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LRB_CHECK(cudaEventCreateWithFlags(&ev_h2d[i], cudaEventDisableTiming));
+            LRB_CHECK(cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+            LRB_CHECK(cudaEventCreateWithFlags(&ev_d2h[i], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+
+    // host in/out: pipelined H2D | kernels | D2H over two slots
+    int run_host(const void* x, size_t n, void* y, size_t* n_out) {
+        if (!committed && commit(1) != 0) return -1;
+        if (stages.empty()) { set_error("graph: no blocks"); return -1; }
+        if (ensure_host_pipeline() != 0) return -1;
+        cudaStream_t s = ctx().stream;
+        const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
+        size_t done = 0, produced = 0;
+        int it = 0;
+        while (done < n) {
+            const int slot = it & 1;
+            size_t nc = n - done < host_chunk ? n - done : host_chunk;
+            size_t mo = max_output(nc);
+            if (nc * isz > d_in_cap[slot] || (mo ? mo : 1) * osz > d_out_cap[slot]) {
+                LRB_CHECK(cudaDeviceSynchronize());
+                if (Block::reserve(&d_in[slot], &d_in_cap[slot], nc * isz) != 0) return -1;
+                if (Block::reserve(&d_out[slot], &d_out_cap[slot], (mo ? mo : 1) * osz) != 0) return -1;
+            }
+            if (it >= 2) LRB_CHECK(cudaStreamWaitEvent(s_h2d, ev_comp[slot], 0));     // d_in[slot] free again
+            LRB_CHECK(cudaMemcpyAsync(d_in[slot], (const char*)x + done * isz, nc * isz, cudaMemcpyHostToDevice, s_h2d));
+            LRB_CHECK(cudaEventRecord(ev_h2d[slot], s_h2d));
+            LRB_CHECK(cudaStreamWaitEvent(s, ev_h2d[slot], 0));
+            if (it >= 2) LRB_CHECK(cudaStreamWaitEvent(s, ev_d2h[slot], 0));          // d_out[slot] drained
+            size_t no = 0;
+            if (run_device(d_in[slot], nc, d_out[slot], &no, s) != 0) return -1;
+            LRB_CHECK(cudaEventRecord(ev_comp[slot], s));
+            LRB_CHECK(cudaStreamWaitEvent(s_d2h, ev_comp[slot], 0));
+            if (no) LRB_CHECK(cudaMemcpyAsync((char*)y + produced * osz, d_out[slot], no * osz, cudaMemcpyDeviceToHost, s_d2h));
+            LRB_CHECK(cudaEventRecord(ev_d2h[slot], s_d2h));
+            produced += no;
+            done += nc;
+            ++it;
+        }
+        LRB_CHECK(cudaStreamSynchronize(s_h2d));
+        LRB_CHECK(cudaStreamSynchronize(s));
+        LRB_CHECK(cudaStreamSynchronize(s_d2h));
+        *n_out = produced;
+        return 0;
+    }
+
+    int reset() {
+        for (Block* b : blocks) if (b->reset() != 0) return -1;
+        for (Block* b : fused) if (b->reset() != 0) return -1;
+        return 0;
+    }
+
+    int seek(uint64_t idx) {
+        if (!committed && commit(1) != 0) return -1;
+        for (Block* b : stages) {
+            if (b->seek(idx) != 0) return -1;
+            idx = b->outputs_before(idx);
+        }
+        return 0;
+    }
+};
+
+}  // namespace lrb
+
+using namespace lrb;
+
+struct lrb200_graph_s { Graph g; };
+
+extern "C" {
+
+lrb200_graph_t* lrb200_graph_create(void) {
+    if (lrb200_device_count() <= 0) { set_error("no CUDA device available; libluaradio_b200 has no CPU fallback"); return nullptr; }
+    if (ctx().device < 0 && lrb200_init(0) != 0) return nullptr;
+    lrb200_graph_t* g = new (std::nothrow) lrb200_graph_s();
+    if (!g) set_error("out of memory");
+    return g;
+}
+
+int lrb200_graph_append(lrb200_graph_t* g, lrb200_block_t* q) {
+    if (!g || !q || !q->impl) { set_error("graph_append: null handle"); return -1; }
+    if (!q->impl->dev_ptrs) { set_error("graph_append: block %s was not created with LRB200_DEVICE", q->impl->name); return -1; }
+    if (!g->g.blocks.empty() && g->g.blocks.back()->out_size != q->impl->in_size) {
+        set_error("graph_append: %s (out %zu B) cannot feed %s (in %zu B)", g->g.blocks.back()->name,
+                  g->g.blocks.back()->out_size, q->impl->name, q->impl->in_size);
+        return -1;
+    }
+    g->g.blocks.push_back(q->impl);
+    g->g.committed = false;
+    q->impl = nullptr;          // ownership moves to the graph
+    delete q;
+    return 0;
+}
+
+int lrb200_graph_commit(lrb200_graph_t* g, int fuse) {
+    if (!g) { set_error("null graph"); return -1; }
+    return g->g.commit(fuse);
+}
+
+int lrb200_graph_execute(lrb200_graph_t* g, const void* x, size_t n, void* y, size_t* n_out) {
+    if (!g) { set_error("null graph"); return -1; }
+    size_t no = 0;
+    int rc = g->g.run_host(x, n, y, &no);
+    if (n_out) *n_out = no;
+    return rc;
+}
+
+int lrb200_graph_execute_device(lrb200_graph_t* g, const void* dx, size_t n, void* dy, size_t* n_out) {
+    if (!g) { set_error("null graph"); return -1; }
+    size_t no = 0;
+    int rc = g->g.run_device(dx, n, dy, &no, ctx().stream);
+    if (n_out) *n_out = no;
+    return rc;
+}
+
+size_t lrb200_graph_max_output(const lrb200_graph_t* g, size_t n) {
+    if (!g) return 0;
+    lrb200_graph_t* gg = const_cast<lrb200_graph_t*>(g);
+    if (!gg->g.committed && gg->g.commit(1) != 0) return 0;
+    return gg->g.max_output(n);
+}
+
+int lrb200_graph_reset(lrb200_graph_t* g) {
+    if (!g) { set_error("null graph"); return -1; }
+    return g->g.reset();
+}
+
+int lrb200_graph_seek(lrb200_graph_t* g, uint64_t sample_index) {
+    if (!g) { set_error("null graph"); return -1; }
+    return g->g.seek(sample_index);
+}
+
+int lrb200_graph_num_stages(const lrb200_graph_t* g) {
+    if (!g) return 0;
+    lrb200_graph_t* gg = const_cast<lrb200_graph_t*>(g);
+    if (!gg->g.committed && gg->g.commit(1) != 0) return -1;
+    return (int)gg->g.stages.size();
+}
+
+const char* lrb200_graph_describe(const lrb200_graph_t* g) {
+    if (!g) return "";
+    lrb200_graph_t* gg = const_cast<lrb200_graph_t*>(g);
+    if (!gg->g.committed && gg->g.commit(1) != 0) return "";
+    return gg->g.desc.c_str();
+}
+
+const char* lrb200_graph_stage_name(const lrb200_graph_t* g, int stage) {
+    if (!g) return "";
+    lrb200_graph_t* gg = const_cast<lrb200_graph_t*>(g);
+    if (!gg->g.committed && gg->g.commit(1) != 0) return "";
+    if (stage < 0 || stage >= (int)gg->g.stages.size()) return "";
+    return gg->g.stages[stage]->name;
+}
+
+int lrb200_graph_set_timing(lrb200_graph_t* g, int enable) {
+    if (!g) { set_error("null graph"); return -1; }
+    g->g.timing = enable != 0;
+    return 0;
+}
+
+double lrb200_graph_stage_time_ms(lrb200_graph_t* g, int stage, int* executions) {
+    if (executions) *executions = 0;
+    if (!g || stage < 0 || stage >= (int)g->g.tcount.size()) return 0.0;
+    if (cudaStreamSynchronize(ctx().stream) != cudaSuccess) return 0.0;
+    double total = 0.0;
+    int cnt = g->g.tcount[stage];
+    for (int i = 0; i < cnt; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g->g.tev[stage][2 * i], g->g.tev[stage][2 * i + 1]) == cudaSuccess) total += ms;
+    }
+    if (executions) *executions = cnt;
+    g->g.tcount[stage] = 0;
+    return total;
+}
+
+void lrb200_graph_destroy(lrb200_graph_t* g) { delete g; }
+
+}  // extern "C"

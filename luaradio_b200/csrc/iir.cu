@@ -1,0 +1,211 @@
+// Single-pole IIR (SinglepoleLowpass/Highpass, FMDeemphasis) as a one-pass block-parallel scan.
+//
+// Reference recurrence (radio/blocks/signal/iirfilter.lua:113-179, liquid iirfilt :79-109):
+//     y[n] = (sum_{j<nb} b[j] x[n-j] - a[1] y[n-1]) / a[0]
+// With u[n] = sum_j (b[j]/a0) x[n-j] and c = -a1/a0 this is the affine recurrence y[n] = c*y[n-1] + u[n].
+// Affine maps compose associatively, and every map here has the same slope c, so the composition over
+// a span of k samples has slope c^k (a host-precomputed constant) and only the offsets need scanning:
+//   thread: V sequential steps -> warp: Kogge-Stone with slopes c^(V*2^k) -> CTA: Horner over warps ->
+//   grid:   decoupled look-back over per-tile (aggregate | inclusive prefix) records.
+// The input is read once and the output written once (8 B/sample real, 16 B/sample complex).
+#include "common.cuh"
+
+namespace lrb {
+
+namespace {
+
+constexpr int IIR_THREADS = 256;
+constexpr int IIR_V = 8;
+constexpr int IIR_TILE = IIR_THREADS * IIR_V;
+constexpr int IIR_MAX_NB = 9;
+
+struct IirParams {
+    float b[IIR_MAX_NB];
+    int nb;
+    float c;
+    float cp[9];   // cp[k] = c^(V * 2^k), k = 0..8 ; cp[8] = c^TILE
+};
+
+__device__ __forceinline__ float zero_of(float) { return 0.f; }
+__device__ __forceinline__ float2 zero_of(float2) { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ float fmas(float c, float v, float a) { return fmaf(c, v, a); }
+__device__ __forceinline__ float2 fmas(float c, float2 v, float2 a) { return __ffma2_rn(v, make_float2(c, c), a); }
+__device__ __forceinline__ float shfl_up_t(float v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ float2 shfl_up_t(float2 v, int d) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ld_cg(const float2* p) { return __ldcg(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(IIR_THREADS)
+iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirParams P,
+                 const T* __restrict__ xhist_in, T* __restrict__ xhist_out,
+                 const T* __restrict__ ystate_in, T* __restrict__ ystate_out,
+                 long long first, int D, int* ticket, volatile int* flags, T* agg, T* pfx, unsigned epoch) {
+    __shared__ int s_tile;
+    __shared__ T s_warp[IIR_THREADS / 32];
+    __shared__ T s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    const long long base = (long long)tile * IIR_TILE + (long long)tid * IIR_V;
+    const int nh = P.nb - 1;
+
+    // ---- u[i] = sum_j b[j] x[i-j] over this thread's V samples (zero beyond n)
+    T xv[IIR_V + IIR_MAX_NB - 1];
+#pragma unroll
+    for (int i = 0; i < IIR_V + IIR_MAX_NB - 1; ++i) {
+        long long idx = base + i - (IIR_MAX_NB - 1);
+        T v = zero_of(T());
+        if (i >= IIR_MAX_NB - 1 - nh) {
+            if (idx >= 0) { if (idx < n) v = __ldg(x + idx); }
+            else if (nh + idx >= 0) v = __ldg(xhist_in + (nh + idx));
+        }
+        xv[i] = v;
+    }
+    T yl[IIR_V];
+#pragma unroll
+    for (int i = 0; i < IIR_V; ++i) {
+        T u = zero_of(T());
+#pragma unroll
+        for (int j = 0; j < IIR_MAX_NB; ++j)
+            if (j < P.nb) u = fmas(P.b[j], xv[i + IIR_MAX_NB - 1 - j], u);
+        yl[i] = (i == 0) ? u : fmas(P.c, yl[i - 1], u);
+    }
+
+    // ---- warp scan of the per-thread zero-state end values
+    T B = yl[IIR_V - 1];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        T o = shfl_up_t(B, 1 << k);
+        if (lane >= (1 << k)) B = fmas(P.cp[k], o, B);
+    }
+    if (lane == 31) s_warp[warp] = B;
+    T prevB = shfl_up_t(B, 1);                      // inclusive value of lane-1 (zero-state from warp start)
+    if (lane == 0) prevB = zero_of(T());
+    __syncthreads();
+    T carryW = zero_of(T());                        // value at the end of warp-1, zero-state from tile start
+    for (int w = 0; w < warp; ++w) carryW = fmas(P.cp[5], carryW, s_warp[w]);
+    float f_lane = 1.f;                             // c^(V*lane)
+#pragma unroll
+    for (int k = 0; k < 5; ++k) if (lane & (1 << k)) f_lane *= P.cp[k];
+    const T excl = fmas(f_lane, carryW, prevB);     // y just before this thread's first sample, zero-state from tile start
+
+    // ---- tile aggregate + decoupled look-back
+    __shared__ T s_agg;
+    if (tid == IIR_THREADS - 1) s_agg = fmas(f_lane * P.cp[0], carryW, B);
+    __syncthreads();
+    if (tid == 0) {
+        T carry_in;
+        if (tile == 0) {
+            carry_in = __ldg(ystate_in);
+        } else {
+            agg[tile] = s_agg;
+            __threadfence();
+            flags[tile] = (int)(epoch * 4u + 1u);
+            T acc = zero_of(T());
+            float mult = 1.f;
+            int j = tile - 1;
+            while (true) {
+                int f;
+                do { f = flags[j]; } while ((unsigned)f >> 2 != epoch);
+                __threadfence();
+                if ((f & 3) == 2) { acc = fmas(mult, ld_cg(pfx + j), acc); break; }
+                acc = fmas(mult, ld_cg(agg + j), acc);
+                mult *= P.cp[8];
+                --j;
+            }
+            carry_in = acc;
+        }
+        T tile_incl = fmas(P.cp[8], carry_in, s_agg);
+        pfx[tile] = tile_incl;
+        __threadfence();
+        flags[tile] = (int)(epoch * 4u + 2u);
+        s_carry = carry_in;
+    }
+    __syncthreads();
+    const T carry_in = s_carry;
+    float f_thread = f_lane;                        // c^(V*tid)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) if (warp & (1 << k)) f_thread *= P.cp[5 + k];
+    const T carry_t = fmas(f_thread, carry_in, excl);
+
+    // ---- outputs y[i] = yl[i] + c^(i+1) * carry_t
+    float cpow = P.c;
+#pragma unroll
+    for (int i = 0; i < IIR_V; ++i) {
+        long long idx = base + i;
+        T v = fmas(cpow, carry_t, yl[i]);
+        cpow *= P.c;
+        if (idx < n) {
+            if (D == 1) {
+                y[idx] = v;
+            } else if (idx >= first && ((idx - first) % D) == 0) {
+                y[(idx - first) / D] = v;
+            }
+            if (idx == n - 1) *ystate_out = v;
+        }
+    }
+    // ---- carried input history for the next call: last nb-1 inputs of [xhist_in | x]
+    if (tile == 0 && tid < nh) {
+        long long i = n - nh + tid;
+        xhist_out[tid] = (i >= 0) ? x[i] : xhist_in[nh + i];
+    }
+}
+
+}  // namespace
+
+int iir_work_alloc(IirScanWork* w, int elem_size) {
+    w->max_tiles = 1 << 15;   // 64 Mi samples per launch
+    LRB_CHECK(cudaMalloc(&w->ticket, sizeof(int)));
+    LRB_CHECK(cudaMalloc(&w->flags, sizeof(int) * w->max_tiles));
+    LRB_CHECK(cudaMalloc(&w->agg, (size_t)elem_size * w->max_tiles));
+    LRB_CHECK(cudaMalloc(&w->pfx, (size_t)elem_size * w->max_tiles));
+    LRB_CHECK(cudaMemset(w->flags, 0, sizeof(int) * w->max_tiles));
+    w->epoch = 0;
+    return 0;
+}
+
+void iir_work_free(IirScanWork* w) {
+    cudaFree(w->ticket); cudaFree(w->flags); cudaFree(w->agg); cudaFree(w->pfx);
+    *w = IirScanWork();
+}
+
+long long iir_max_per_launch(const IirScanWork& w) { return (long long)w.max_tiles * IIR_TILE; }
+
+int launch_iir1(bool complex_data, const void* x, long long n, void* y, const float* b_host, int nb, float c,
+                const void* xhist_in, void* xhist_out, const void* ystate_in, void* ystate_out,
+                long long first, int D, IirScanWork* w, cudaStream_t s) {
+    if (n <= 0) return 0;
+    if (nb < 1 || nb > IIR_MAX_NB) { set_error("iir: nb must be in 1..%d", IIR_MAX_NB); return -1; }
+    if (n > iir_max_per_launch(*w)) { set_error("iir: chunk too large for one launch"); return -1; }
+    IirParams P;
+    for (int j = 0; j < IIR_MAX_NB; ++j) P.b[j] = j < nb ? b_host[j] : 0.f;
+    P.nb = nb;
+    P.c = c;
+    double cd = (double)c, p = 1.0;
+    for (int i = 0; i < IIR_V; ++i) p *= cd;      // c^V
+    for (int k = 0; k < 9; ++k) { P.cp[k] = (float)p; p = p * p; }
+    w->epoch = (w->epoch + 1) & 0x3fffffffu;
+    if (w->epoch == 0) {                          // wrapped: clear stale flags
+        LRB_CHECK(cudaMemsetAsync(w->flags, 0, sizeof(int) * w->max_tiles, s));
+        w->epoch = 1;
+    }
+    LRB_CHECK(cudaMemsetAsync(w->ticket, 0, sizeof(int), s));
+    int tiles = (int)((n + IIR_TILE - 1) / IIR_TILE);
+    if (complex_data)
+        iir1_scan_kernel<float2><<<tiles, IIR_THREADS, 0, s>>>((const float2*)x, n, (float2*)y, P,
+            (const float2*)xhist_in, (float2*)xhist_out, (const float2*)ystate_in, (float2*)ystate_out,
+            first, D, w->ticket, w->flags, (float2*)w->agg, (float2*)w->pfx, w->epoch);
+    else
+        iir1_scan_kernel<float><<<tiles, IIR_THREADS, 0, s>>>((const float*)x, n, (float*)y, P,
+            (const float*)xhist_in, (float*)xhist_out, (const float*)ystate_in, (float*)ystate_out,
+            first, D, w->ticket, w->flags, (float*)w->agg, (float*)w->pfx, w->epoch);
+    count_launch();
+    LRB_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace lrb

@@ -1,0 +1,139 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every declared symbol, product tap
+design matches the reference's golden vectors, flow-graph construction follows the reference's rules,
+and every compute entry point fails LOUDLY without a CUDA device (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import luaradio_b200 as radio
+from luaradio_b200 import _lib
+from luaradio_b200.types import ComplexFloat32, Float32, Vector
+from tests.golden_util import GOLDEN_DIR, epsilon_ok
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        return _lib.load().lrb200_device_count() > 0
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lrb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(lrb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) > 40
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), "declared in include/lrb200.h but not exported: " + name
+    assert set(declared) == set(_lib.EXPORTED_SYMBOLS), set(declared) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert b"sm_100a" in lib.lrb200_version()
+
+
+def test_no_cpu_fallback_without_device():
+    if _have_gpu():
+        pytest.skip("a GPU is present")
+    lib = _lib.load()
+    assert lib.lrb200_init(0) != 0
+    assert b"no CPU fallback" in lib.lrb200_last_error()
+    taps = np.ones(4, np.float32)
+    assert not lib.lrb200_fir_create_crcf(taps.ctypes.data, 4, 1, 0)
+    assert not lib.lrb200_graph_create()
+    blk = radio.LowpassFilterBlock(128, 0.2)
+    blk.get_rate = lambda: 2.0
+    blk.differentiate([ComplexFloat32])
+    with pytest.raises(_lib.LibraryError):
+        blk.initialize()
+
+
+def test_product_tap_design_matches_reference_vectors():
+    fu = radio.filter_utils
+    z = np.load(GOLDEN_DIR + "/filter_utils_vectors.npz")
+    cases = {
+        "firwin_lowpass": fu.firwin_lowpass(128, 0.5), "firwin_highpass": fu.firwin_highpass(129, 0.5),
+        "firwin_bandpass": fu.firwin_bandpass(129, [0.4, 0.6]), "firwin_bandstop": fu.firwin_bandstop(129, [0.4, 0.6]),
+        "firwin_complex_bandpass_positive": fu.firwin_complex_bandpass(129, [0.1, 0.3]),
+        "firwin_complex_bandpass_negative": fu.firwin_complex_bandpass(129, [-0.1, -0.3]),
+        "firwin_complex_bandpass_zero": fu.firwin_complex_bandpass(129, [-0.2, 0.2]),
+        "firwin_complex_bandstop_positive": fu.firwin_complex_bandstop(129, [0.1, 0.3]),
+        "firwin_complex_bandstop_negative": fu.firwin_complex_bandstop(129, [-0.1, -0.3]),
+        "firwin_complex_bandstop_zero": fu.firwin_complex_bandstop(129, [-0.2, 0.2]),
+        "fir_hilbert_transform": fu.fir_hilbert_transform(129),
+    }
+    for k, h in cases.items():
+        h = np.asarray(h)
+        h = h.astype(np.complex64 if np.iscomplexobj(h) else np.float32)
+        ok, msg = epsilon_ok(h, z[k], 1e-6)
+        assert ok, "%s: %s" % (k, msg)
+    w = np.load(GOLDEN_DIR + "/window_utils_vectors.npz")
+    for name in ("rectangular", "hamming", "hanning", "bartlett", "blackman"):
+        for per in (False, True):
+            key = "window_" + name + ("_periodic" if per else "")
+            ok, msg = epsilon_ok(np.array(radio.window_utils.window(len(w[key]), name, per), np.float32), w[key], 1e-6)
+            assert ok, "%s: %s" % (key, msg)
+
+
+def test_type_signatures_and_differentiate():
+    f = radio.FIRFilterBlock([0.2] * 5)
+    f.differentiate([Float32])
+    assert f.get_output_type() is Float32
+    f = radio.FIRFilterBlock([0.2] * 5)
+    f.differentiate([ComplexFloat32])
+    assert f.get_output_type() is ComplexFloat32
+    f = radio.FIRFilterBlock(ComplexFloat32.vector_from_array([1 + 1j, 0.5]))
+    with pytest.raises(AssertionError):
+        f.differentiate([Float32])            # complex taps have no real-input signature (firfilter.lua:68-73)
+    d = radio.FrequencyDiscriminatorBlock(1.25)
+    d.differentiate([ComplexFloat32])
+    assert d.get_output_type() is Float32
+    with pytest.raises(AssertionError):
+        radio.HilbertTransformBlock(128)      # even tap count
+    with pytest.raises(AssertionError):
+        radio.FrequencyTranslatorBlock(None)
+
+
+def test_composite_graph_building_and_rates():
+    src = radio.ArraySource(np.zeros(100, np.complex64), 1102500.0)
+    snk = radio.ArraySink()
+    top = radio.CompositeBlock()
+    tuner = radio.TunerBlock(-250e3, 200e3, 5)
+    ds = radio.DownsamplerBlock(5)
+    top.connect(src, tuner, radio.FrequencyDiscriminatorBlock(1.25), radio.LowpassFilterBlock(128, 15e3),
+                radio.FMDeemphasisFilterBlock(75e-6), ds, snk)
+    top._validate_inputs()
+    top._differentiate()
+    conns = top._crawl_connections()
+    # hierarchical tuner flattened to its three concrete blocks: 7 blocks + sink input => 8 edges
+    assert len(conns) == 8
+    for inp, outp in conns.items():
+        p = radio.block.Pipe(outp, inp)
+        outp.pipes.append(p)
+        inp.pipe = p
+    assert snk.get_rate() == pytest.approx(1102500.0 / 25)
+    assert ds.inputs[0].pipe.get_rate() == pytest.approx(220500.0)
+    # an unconnected input is an error (composite.lua:302-312)
+    top2 = radio.CompositeBlock()
+    a, b = radio.FrequencyTranslatorBlock(1.0), radio.ComplexMagnitudeBlock()
+    top2.connect(a, b)
+    with pytest.raises(AssertionError):
+        top2._validate_inputs()
+    # an input can only be driven once
+    with pytest.raises(AssertionError):
+        top2.connect(radio.FrequencyTranslatorBlock(2.0), "out", b, "in")
+
+
+def test_vector_semantics():
+    v = ComplexFloat32.vector(4)
+    assert v.length == 4 and v.size == 32 and np.all(v.data == 0)
+    v.resize(2)
+    assert v.length == 2
+    v.resize(6)
+    assert v.length == 6 and v.data.dtype == np.complex64
+    f = Float32.vector_from_array([1, 2, 3])
+    assert f.size == 12
+    c = Vector.cast(np.arange(4, dtype=np.float32))
+    assert c.data_type is Float32 and c.length == 4
