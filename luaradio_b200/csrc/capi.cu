@@ -164,8 +164,7 @@ RotatorBlock::RotatorBlock(double turns_per_sample, bool dev) {
     in_size = out_size = 8;
     dev_ptrs = dev;
     turns = turns_per_sample;
-    double t = turns_per_sample - std::floor(turns_per_sample);   // [0,1)
-    turns_fix = (uint64_t)std::ldexp(t, 64);
+    turns_fix = turns_to_fix(turns_per_sample);
 }
 
 int RotatorBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <atomic>
+#include <math.h>
 
 namespace lrb {
 
@@ -23,6 +24,17 @@ bool cuda_ok(cudaError_t e, const char* what);
     do {                                                  \
         if (!::lrb::cuda_ok((call), #call)) return -1;    \
     } while (0)
+
+// cycles-per-sample (any sign / magnitude) -> fraction of a turn in 2^-64 units.  Done in 80-bit long double
+// so that removing the integer part does not round the 53-bit fraction (a 2^-54 error per sample is
+// 3e-6 rad after 2^33 samples).
+inline uint64_t turns_to_fix(double turns) {
+    long double t = (long double)turns;
+    t -= floorl(t);                         // [0,1), exact
+    long double f = ldexpl(t, 64);
+    if (f >= 18446744073709551616.0L) return 0;
+    return (uint64_t)f;
+}
 
 inline void count_launch(int n = 1) { ctx().launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

@@ -14,16 +14,18 @@ namespace lrb {
 
 namespace {
 
-constexpr int IIR_THREADS = 256;
+constexpr int IIR_THREADS = 512;
+constexpr int IIR_LOGW = 4;                 // log2(warps per CTA)
 constexpr int IIR_V = 8;
 constexpr int IIR_TILE = IIR_THREADS * IIR_V;
+static_assert((32 << IIR_LOGW) == IIR_THREADS, "IIR_LOGW must be log2(warps per CTA)");
 constexpr int IIR_MAX_NB = 9;
 
 struct IirParams {
     float b[IIR_MAX_NB];
     int nb;
     float c;
-    float cp[9];   // cp[k] = c^(V * 2^k), k = 0..8 ; cp[8] = c^TILE
+    float cp[5 + IIR_LOGW + 1];   // cp[k] = c^(V * 2^k); cp[5 + LOGW] = c^TILE
 };
 
 __device__ __forceinline__ float zero_of(float) { return 0.f; }
@@ -34,6 +36,12 @@ __device__ __forceinline__ float shfl_up_t(float v, int d) { return __shfl_up_sy
 __device__ __forceinline__ float2 shfl_up_t(float2 v, int d) {
     return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
 }
+__device__ __forceinline__ float shfl_xor_t(float v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ float2 shfl_xor_t(float2 v, int d) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, d), __shfl_xor_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ float add_t(float a, float b) { return a + b; }
+__device__ __forceinline__ float2 add_t(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float2 ld_cg(const float2* p) { return __ldcg(p); }
 
@@ -93,43 +101,62 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     for (int k = 0; k < 5; ++k) if (lane & (1 << k)) f_lane *= P.cp[k];
     const T excl = fmas(f_lane, carryW, prevB);     // y just before this thread's first sample, zero-state from tile start
 
-    // ---- tile aggregate + decoupled look-back
+    // ---- tile aggregate + decoupled look-back.  The whole of warp 0 walks back 32 predecessor tiles at a
+    // time (warp-uniform control flow: a single spinning lane in front of __syncthreads() is NOT safe).
     __shared__ T s_agg;
     if (tid == IIR_THREADS - 1) s_agg = fmas(f_lane * P.cp[0], carryW, B);
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+        const float cT = P.cp[5 + IIR_LOGW];
         T carry_in;
         if (tile == 0) {
             carry_in = __ldg(ystate_in);
         } else {
-            agg[tile] = s_agg;
-            __threadfence();
-            flags[tile] = (int)(epoch * 4u + 1u);
+            if (lane == 0) {
+                agg[tile] = s_agg;
+                __threadfence();
+                flags[tile] = (int)(epoch * 4u + 1u);
+            }
+            __syncwarp();
+            float wl = 1.f, pw = cT;                // wl = cT^lane, pw -> cT^32
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { if (lane & (1 << k)) wl *= pw; pw *= pw; }
             T acc = zero_of(T());
             float mult = 1.f;
-            int j = tile - 1;
+            int jbase = tile - 1;
             while (true) {
-                int f;
-                do { f = flags[j]; } while ((unsigned)f >> 2 != epoch);
-                __threadfence();
-                if ((f & 3) == 2) { acc = fmas(mult, ld_cg(pfx + j), acc); break; }
-                acc = fmas(mult, ld_cg(agg + j), acc);
-                mult *= P.cp[8];
-                --j;
+                const int j = jbase - lane;
+                int f = 0;
+                T v = zero_of(T());
+                if (j >= 0) {
+                    do { f = flags[j]; } while ((unsigned)f >> 2 != epoch);
+                    __threadfence();
+                    v = ((f & 3) == 2) ? ld_cg(pfx + j) : ld_cg(agg + j);
+                }
+                const unsigned pmask = __ballot_sync(0xffffffffu, j >= 0 && (f & 3) == 2);
+                const int last = pmask ? (__ffs(pmask) - 1) : 31;    // nearest tile that already has its inclusive prefix
+                T contrib = (j >= 0 && lane <= last) ? fmas(wl, v, zero_of(T())) : zero_of(T());
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) contrib = add_t(contrib, shfl_xor_t(contrib, off));
+                acc = fmas(mult, contrib, acc);
+                if (pmask) break;                   // tile 0 always publishes a prefix, so this terminates
+                mult *= pw;
+                jbase -= 32;
             }
             carry_in = acc;
         }
-        T tile_incl = fmas(P.cp[8], carry_in, s_agg);
-        pfx[tile] = tile_incl;
-        __threadfence();
-        flags[tile] = (int)(epoch * 4u + 2u);
-        s_carry = carry_in;
+        if (lane == 0) {
+            pfx[tile] = fmas(cT, carry_in, s_agg);
+            __threadfence();
+            flags[tile] = (int)(epoch * 4u + 2u);
+            s_carry = carry_in;
+        }
     }
     __syncthreads();
     const T carry_in = s_carry;
     float f_thread = f_lane;                        // c^(V*tid)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) if (warp & (1 << k)) f_thread *= P.cp[5 + k];
+    for (int k = 0; k < IIR_LOGW; ++k) if (warp & (1 << k)) f_thread *= P.cp[5 + k];
     const T carry_t = fmas(f_thread, carry_in, excl);
 
     // ---- outputs y[i] = yl[i] + c^(i+1) * carry_t
@@ -158,7 +185,7 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
 }  // namespace
 
 int iir_work_alloc(IirScanWork* w, int elem_size) {
-    w->max_tiles = 1 << 15;   // 64 Mi samples per launch
+    w->max_tiles = 1 << 15;   // 128 Mi samples per launch
     LRB_CHECK(cudaMalloc(&w->ticket, sizeof(int)));
     LRB_CHECK(cudaMalloc(&w->flags, sizeof(int) * w->max_tiles));
     LRB_CHECK(cudaMalloc(&w->agg, (size_t)elem_size * w->max_tiles));
@@ -187,7 +214,7 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
     P.c = c;
     double cd = (double)c, p = 1.0;
     for (int i = 0; i < IIR_V; ++i) p *= cd;      // c^V
-    for (int k = 0; k < 9; ++k) { P.cp[k] = (float)p; p = p * p; }
+    for (int k = 0; k < 5 + IIR_LOGW + 1; ++k) { P.cp[k] = (float)p; p = p * p; }
     w->epoch = (w->epoch + 1) & 0x3fffffffu;
     if (w->epoch == 0) {                          // wrapped: clear stale flags
         LRB_CHECK(cudaMemsetAsync(w->flags, 0, sizeof(int) * w->max_tiles, s));

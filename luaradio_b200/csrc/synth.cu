@@ -63,9 +63,7 @@ int launch_synth_white(float2* dst, uint64_t n0, long long n, uint32_t seed, cud
 int launch_synth_fm(float2* dst, uint64_t n0, long long n, uint32_t seed, double rate, double carrier,
                     double deviation, float amp, float noise, cudaStream_t s) {
     if (n <= 0) return 0;
-    double turns = carrier / rate;
-    turns -= floor(turns);
-    uint64_t fix = (uint64_t)ldexp(turns, 64);   // turns in [0,1) -> 2^64 fixed point (exact for a double)
+    uint64_t fix = turns_to_fix(carrier / rate);
     int blocks = ctx().sm_count * 8;
     synth_fm_kernel<<<blocks, 256, 0, s>>>(dst, n0, n, seed, rate, fix, deviation, amp, noise);
     count_launch();

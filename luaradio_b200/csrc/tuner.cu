@@ -210,8 +210,7 @@ PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sa
     }
     p->P.M = M;
     const double two_pi = 6.283185307179586476925286766559;
-    double t = turns_per_sample - std::floor(turns_per_sample);
-    p->P.turns_fix = (uint64_t)std::ldexp(t, 64);
+    p->P.turns_fix = turns_to_fix(turns_per_sample);
     // staging-step phasors from the SAME fixed-point turns the kernel uses for the absolute phase
     const double tq = std::ldexp((double)p->P.turns_fix, -64);
     for (int it = 0; it < PT_MAXIT; ++it) {
