@@ -48,10 +48,16 @@ __device__ __forceinline__ float2 cmul_conj_if(float2 a, float2 w, bool conj) {
 }
 
 // MODE 0: complex input / complex output (crcf, cccf).  MODE 1: real input packed two blocks per FFT (rrrf).
-template <int MODE>
+// EDGE false: interior blocks [b_lo, b_hi) whose N inputs and L outputs all lie inside x / y: unconditional,
+//             fully coalesced loads and stores, one code path (the compiler otherwise clones the butterfly
+//             networks behind each branch of a guarded load).
+// EDGE true : the few blocks that touch the carried history (b = 0) or the end of the input (b >= b_hi):
+//             edge index e = 0 -> block 0, e >= 1 -> block b_hi + e - 1; every access is bounds-checked.
+template <int MODE, bool EDGE>
 __global__ void __launch_bounds__(FF_THREADS, 2)
 fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, long long n, void* __restrict__ yv,
-                   const float2* __restrict__ Hg, const float2* __restrict__ twg, int M, long long nblocks) {
+                   const float2* __restrict__ Hg, const float2* __restrict__ twg, int M, long long b_lo, long long b_hi,
+                   long long nwork) {
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw = sm;                            // [k1][n2]  W1024^(k1*n2)
     float2* s_H = sm + FF_N;                      // [k2][k1]  H[k1 + 32 k2] / N
@@ -63,16 +69,18 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
     const int L = FF_N - (M - 1);
     const int Hm1 = M - 1;
     const long long wstride = (long long)gridDim.x * FF_WARPS;
-    for (long long b = (long long)blockIdx.x * FF_WARPS + warp; b < nblocks; b += wstride) {
+    for (long long wi = (long long)blockIdx.x * FF_WARPS + warp; wi < nwork; wi += wstride) {
+        const long long b = EDGE ? (wi == 0 ? 0 : b_hi + wi - 1) : (b_lo + wi);
         float2 v[32];
         // ---- load: v[r] = X[base + 32 r + lane]
         if constexpr (MODE == 0) {
             const float2* x = reinterpret_cast<const float2*>(xv);
             const float2* hist = reinterpret_cast<const float2*>(histv);
             const long long base = b * L - Hm1;
-            if (base >= 0 && base + FF_N <= n) {
+            if constexpr (!EDGE) {
+                const float2* xb = x + base + lane;
 #pragma unroll
-                for (int r = 0; r < 32; ++r) v[r] = __ldcs(x + base + 32 * r + lane);
+                for (int r = 0; r < 32; ++r) v[r] = __ldcs(xb + 32 * r);
             } else {
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
@@ -88,9 +96,13 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
                 const long long i0 = base0 + 32 * r + lane, i1 = base1 + 32 * r + lane;
-                const float a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : 0.f) : __ldg(hist + (Hm1 + i0));
-                const float c = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : 0.f) : __ldg(hist + (Hm1 + i1));
-                v[r] = make_float2(a, c);
+                if constexpr (!EDGE) {
+                    v[r] = make_float2(__ldcs(x + i0), __ldcs(x + i1));
+                } else {
+                    const float a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : 0.f) : __ldg(hist + (Hm1 + i0));
+                    const float c = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : 0.f) : __ldg(hist + (Hm1 + i1));
+                    v[r] = make_float2(a, c);
+                }
             }
         }
 
@@ -134,7 +146,7 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
             for (int n1 = 0; n1 < 32; ++n1) {
                 const int nn = 32 * n1 + lane;
                 const long long o = obase + nn;
-                if (nn >= Hm1 && o < n) __stcs(y + o, v[bitrev5(n1)]);
+                if (nn >= Hm1 && (!EDGE || o < n)) __stcs(y + o, v[bitrev5(n1)]);
             }
         } else {
             float* y = reinterpret_cast<float*>(yv);
@@ -144,8 +156,8 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
                 const int nn = 32 * n1 + lane;
                 if (nn >= Hm1) {
                     const float2 t = v[bitrev5(n1)];
-                    if (obase0 + nn < n) y[obase0 + nn] = t.x;
-                    if (obase1 + nn < n) y[obase1 + nn] = t.y;
+                    if (!EDGE || obase0 + nn < n) y[obase0 + nn] = t.x;
+                    if (!EDGE || obase1 + nn < n) y[obase1 + nn] = t.y;
                 }
             }
         }
@@ -238,23 +250,38 @@ int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long
     const int L = FF_N - (M - 1);
     // a forced FFT always runs; the automatic choice leaves short calls (a few blocks) to the direct kernel
     if (algo != LRB200_FIR_FFT && (long long)n < 8LL * L) return 0;
-    long long nblocks = ((long long)n + L - 1) / L;
-    if (fast->mode == 1) nblocks = (nblocks + 1) / 2;
-    auto kern0 = fir_fft1024_kernel<0>;
-    auto kern1 = fir_fft1024_kernel<1>;
+    // blocks of L outputs; in packed-real mode one FFT covers two of them
+    const long long per = (fast->mode == 1) ? 2LL * L : (long long)L;
+    const long long nblocks = ((long long)n + per - 1) / per;
+    long long b_hi = (long long)n / per;                 // blocks [1, b_hi) are interior
+    if (b_hi < 1) b_hi = 1;
+    if (b_hi > nblocks) b_hi = nblocks;
+    const long long n_int = b_hi - 1, n_edge = 1 + (nblocks - b_hi);
     if (!fast->configured) {
-        LRB_CHECK(cudaFuncSetAttribute(kern0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
-        LRB_CHECK(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
+        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
         fast->configured = true;
     }
-    long long ctas = (nblocks + FF_WARPS - 1) / FF_WARPS;
     const long long max_ctas = (long long)ctx().sm_count * 2;
-    if (ctas > max_ctas) ctas = max_ctas;
-    if (fast->mode == 0)
-        kern0<<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, nblocks);
-    else
-        kern1<<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, nblocks);
-    count_launch();
+    if (n_int > 0) {
+        long long ctas = (n_int + FF_WARPS - 1) / FF_WARPS;
+        if (ctas > max_ctas) ctas = max_ctas;
+        if (fast->mode == 0)
+            fir_fft1024_kernel<0, false><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_int);
+        else
+            fir_fft1024_kernel<1, false><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_int);
+        count_launch();
+    }
+    {
+        long long ctas = (n_edge + FF_WARPS - 1) / FF_WARPS;
+        if (fast->mode == 0)
+            fir_fft1024_kernel<0, true><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_edge);
+        else
+            fir_fft1024_kernel<1, true><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_edge);
+        count_launch();
+    }
     LRB_CHECK(cudaGetLastError());
     return 1;
 }
