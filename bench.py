@@ -222,6 +222,11 @@ def run_b200(args):
     ms_step = float(tt.item()) / args.steps
     value = world * n / (ms_step * 1e-3) / 1e6          # M input-samples/s, whole job
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "stages_ms": dict(stage_ms)}))
+            bench_fir128(lib, _lib, torch, stream, args)
+        return
     # ---- e2e: HOST buffers through the C ABI (pinned in, host out), H2D/D2H inside the timed call
     hin = lib.lrb200_host_alloc((n + lead) * 8)
     hout = lib.lrb200_host_alloc((n_out_max + 16) * 4)
@@ -421,6 +426,7 @@ def main():
     ap.add_argument("--samples", type=int, default=268435450, help="input samples per GPU per step (multiple of 25; 256 Mi)")
     ap.add_argument("--fir-samples", type=int, default=1 << 28)
     ap.add_argument("--cpu-samples", type=int, default=1 << 26)
+    ap.add_argument("--profile", action="store_true", help="profiling run (ncu): skip the e2e, FIR-128 sweep and CPU legs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -126,15 +126,19 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
             int jbase = tile - 1;
             while (true) {
                 const int j = jbase - lane;
+                // a predecessor whose weight c^(distance) is below float32 resolution cannot change the result:
+                // it is treated as a (zero) prefix, which cuts the serial tile-to-tile dependency for every
+                // pole whose memory is shorter than a tile (FM de-emphasis: c^4096 underflows to 0).
+                const bool dead = fabsf(wl * mult) < 1e-12f;
                 int f = 0;
                 T v = zero_of(T());
-                if (j >= 0) {
+                if (j >= 0 && !dead) {
                     do { f = flags[j]; } while ((unsigned)f >> 2 != epoch);
                     __threadfence();
                     v = ((f & 3) == 2) ? ld_cg(pfx + j) : ld_cg(agg + j);
                 }
-                const unsigned pmask = __ballot_sync(0xffffffffu, j >= 0 && (f & 3) == 2);
-                const int last = pmask ? (__ffs(pmask) - 1) : 31;    // nearest tile that already has its inclusive prefix
+                const unsigned pmask = __ballot_sync(0xffffffffu, j >= 0 && (dead || (f & 3) == 2));
+                const int last = pmask ? (__ffs(pmask) - 1) : 31;    // nearest tile that ends the walk
                 T contrib = (j >= 0 && lane <= last) ? fmas(wl, v, zero_of(T())) : zero_of(T());
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) contrib = add_t(contrib, shfl_xor_t(contrib, off));

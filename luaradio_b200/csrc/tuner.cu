@@ -55,15 +55,23 @@ struct PolyShape {
     static constexpr size_t SMEM = (size_t)D * JP * sizeof(float2);
 };
 
-template <int D, int Q, bool ROT>
+// EDGE false: interior tiles -- every staged input lies inside x and x is 16-byte aligned, so the stage is
+//             batches of unconditional 128-bit streaming loads issued back to back (7 in flight per thread)
+//             before any of them is consumed.  (The first version guarded every load; ncu showed 85 % of the
+//             stall samples on the first use of each load, i.e. one load in flight per thread.)
+// EDGE true : tiles that touch the carried history or the end of the input; tile index = tile_ids-free mapping
+//             e -> (e < n_head ? e : t_hi + (e - n_head)); every load is bounds-checked.
+template <int D, int Q, bool ROT, bool EDGE>
 __global__ void __launch_bounds__(PT_THREADS)
 polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, long long n,
                       float2* __restrict__ y, long long first, long long n_out,
-                      const __grid_constant__ PolyParams P, int vec_ok) {
+                      const __grid_constant__ PolyParams P, long long t_lo, long long t_hi) {
     using S = PolyShape<D, Q>;
     extern __shared__ __align__(16) float2 smem[];
     const int tid = threadIdx.x;
-    const long long m0 = (long long)blockIdx.x * PT_TO;
+    const long long tile = EDGE ? ((long long)blockIdx.x < t_lo ? (long long)blockIdx.x : t_hi + ((long long)blockIdx.x - t_lo))
+                                : (t_lo + (long long)blockIdx.x);
+    const long long m0 = tile * PT_TO;
     const int M = P.M;
     // first input index needed by output m0 with the taps padded to Q*D at the OLD end:
     // y[m] = sum_{i'} hr[i'] X[c_m - (Q*D - 1) + i'],  c_m = first + m*D
@@ -80,37 +88,62 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         c1 = cmul(c0, P.rot1);
     }
     const int Hm1 = M - 1;
-#pragma unroll 4
-    for (int it = 0; it < S::ITERS; ++it) {
-        const int u = tid + it * PT_THREADS;          // pair index within the tile
-        if (u >= S::PAIRS) break;
-        const long long i0 = Beven + 2LL * u;         // logical input index of the pair's first sample
-        float2 a, b;
-        if (vec_ok && i0 >= 0 && i0 + 1 < n) {
-            float4 v = __ldcs(reinterpret_cast<const float4*>(x + i0));
-            a = make_float2(v.x, v.y);
-            b = make_float2(v.z, v.w);
-        } else {
-            a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : make_float2(0.f, 0.f))
-                          : ((Hm1 + i0 >= 0) ? __ldg(hist + (Hm1 + i0)) : make_float2(0.f, 0.f));
+    // tile-relative index of the pair's first sample, e0 = 2u - shift, tracked as (j, p) = (e0 / D, e0 % D);
+    // one staging iteration advances e0 by 2*PT_THREADS
+    constexpr int ADV_J = (2 * PT_THREADS) / D, ADV_P = (2 * PT_THREADS) % D;
+    int ej, ep;
+    {
+        const int e0 = 2 * tid - shift + D;           // + D keeps the division non-negative (e0 >= -1)
+        ej = e0 / D - 1;
+        ep = e0 - (ej + 1) * D;
+    }
+    auto scatter = [&](float2 a, float2 b) {
+        if (ej >= 0 && ej < S::J) smem[ep * S::JP + pad_idx(ej)] = a;
+        int j1 = ej, p1 = ep + 1;
+        if (p1 == D) { p1 = 0; ++j1; }
+        if (j1 >= 0 && j1 < S::J) smem[p1 * S::JP + pad_idx(j1)] = b;
+        ej += ADV_J;
+        ep += ADV_P;
+        if (ep >= D) { ep -= D; ++ej; }
+    };
+    if constexpr (!EDGE) {
+        constexpr int BATCH = 7;
+        const float4* x4 = reinterpret_cast<const float4*>(x + Beven) + tid;
+#pragma unroll 1
+        for (int it0 = 0; it0 < S::ITERS; it0 += BATCH) {
+            float4 buf[BATCH];
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k)
+                if (it0 + k < S::ITERS) buf[k] = __ldcs(x4 + (it0 + k) * PT_THREADS);
+#pragma unroll
+            for (int k = 0; k < BATCH; ++k) {
+                if (it0 + k < S::ITERS) {
+                    float2 a = make_float2(buf[k].x, buf[k].y), b = make_float2(buf[k].z, buf[k].w);
+                    if constexpr (ROT) {
+                        const float2 st = P.step[it0 + k];
+                        a = cmul(a, cmul(c0, st));
+                        b = cmul(b, cmul(c1, st));
+                    }
+                    scatter(a, b);
+                }
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int it = 0; it < S::ITERS; ++it) {
+            const int u = tid + it * PT_THREADS;      // pair index within the tile
+            const long long i0 = Beven + 2LL * u;     // logical input index of the pair's first sample
+            float2 a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : make_float2(0.f, 0.f))
+                                 : ((Hm1 + i0 >= 0) ? __ldg(hist + (Hm1 + i0)) : make_float2(0.f, 0.f));
             const long long i1 = i0 + 1;
-            b = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : make_float2(0.f, 0.f))
-                          : ((Hm1 + i1 >= 0) ? __ldg(hist + (Hm1 + i1)) : make_float2(0.f, 0.f));
-        }
-        if constexpr (ROT) {
-            const float2 st = P.step[it];
-            a = cmul(a, cmul(c0, st));
-            b = cmul(b, cmul(c1, st));
-        }
-        // tile-relative index (relative to B): e = 2u - shift (+1)
-        const int e0 = 2 * u - shift, e1 = e0 + 1;
-        if (e0 >= 0) {
-            const int j = e0 / D, p = e0 - j * D;
-            if (j < S::J) smem[p * S::JP + pad_idx(j)] = a;
-        }
-        {
-            const int j = e1 / D, p = e1 - j * D;
-            if (j < S::J) smem[p * S::JP + pad_idx(j)] = b;
+            float2 b = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : make_float2(0.f, 0.f))
+                                 : ((Hm1 + i1 >= 0) ? __ldg(hist + (Hm1 + i1)) : make_float2(0.f, 0.f));
+            if constexpr (ROT) {
+                const float2 st = P.step[it];
+                a = cmul(a, cmul(c0, st));
+                b = cmul(b, cmul(c1, st));
+            }
+            scatter(a, b);
         }
     }
     __syncthreads();
@@ -168,15 +201,36 @@ int launch_shape(const PolyParams& P, const float2* x, const float2* hist, long 
     static_assert(Q * D <= PT_MAXTAPS, "taps table too small");
     static_assert(S::ITERS <= PT_MAXIT, "step table too small");
     static bool configured = false;
-    auto kern = polyphase_crcf_kernel<D, Q, ROT>;
+    auto kern_i = polyphase_crcf_kernel<D, Q, ROT, false>;
+    auto kern_e = polyphase_crcf_kernel<D, Q, ROT, true>;
     if (!configured) {
-        LRB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        LRB_CHECK(cudaFuncSetAttribute(kern_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
+        LRB_CHECK(cudaFuncSetAttribute(kern_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         configured = true;
     }
-    long long tiles = (n_out + PT_TO - 1) / PT_TO;
-    int vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
-    kern<<<(unsigned)tiles, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, first, n_out, P, vec_ok);
-    count_launch();
+    const long long tiles = (n_out + PT_TO - 1) / PT_TO;
+    // interior tiles: staged span [Beven, Beven + 2*ITERS*THREADS) inside [0, n), x 16-byte aligned
+    long long t_lo = 0, t_hi = 0;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const long long span = 2LL * S::ITERS * PT_THREADS;
+        // Beven(t) >= B(t) - 1,  B(t) = first + t*TO*D - (Q*D - 1)
+        const long long step = (long long)PT_TO * D;
+        const long long need_lo = (long long)(Q * D - 1) + 1 - first;            // B(t) - 1 >= 0
+        t_lo = need_lo <= 0 ? 0 : (need_lo + step - 1) / step;
+        const long long lim = n - span - first + (long long)(Q * D - 1);         // B(t) + span <= n
+        t_hi = lim < 0 ? 0 : lim / step + 1;
+        if (t_hi > tiles) t_hi = tiles;
+        if (t_lo > t_hi) t_lo = t_hi;
+    }
+    const long long n_int = t_hi - t_lo, n_edge = tiles - n_int;
+    if (n_int > 0) {
+        kern_i<<<(unsigned)n_int, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, first, n_out, P, t_lo, t_hi);
+        count_launch();
+    }
+    if (n_edge > 0) {
+        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, first, n_out, P, t_lo, t_hi);
+        count_launch();
+    }
     LRB_CHECK(cudaGetLastError());
     return 1;
 }
