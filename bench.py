@@ -142,7 +142,7 @@ def build_chain_graph(lib, _lib):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from luaradio_b200 import _lib
+    from luaradio_b200 import _lib, sharding
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -173,14 +173,7 @@ def run_b200(args):
 
     def step():
         if world > 1:
-            ops = []
-            if rank + 1 < world:
-                ops.append(dist.P2POp(dist.isend, x[HALO + n - HALO:HALO + n], rank + 1))
-            if rank > 0:
-                ops.append(dist.P2POp(dist.irecv, x[0:HALO], rank - 1))
-            if ops:
-                for r in dist.batch_isend_irecv(ops):
-                    r.wait()
+            sharding.exchange_halo(dist, x[HALO:HALO + n], x[0:HALO], rank, world, HALO)
         _lib.check(lib.lrb200_graph_reset(g), "reset")
         _lib.check(lib.lrb200_graph_seek(g, start - lead), "seek")
         _lib.check(lib.lrb200_graph_execute_device(g, ctypes.c_void_p(xp + (HALO - lead) * 8), n + lead,

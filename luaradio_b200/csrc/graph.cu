@@ -5,7 +5,7 @@
 // in a two-slot device ring; host<->device traffic exists only at the two ends, double-buffered on
 // separate copy streams so chunk i+1 uploads while chunk i computes and chunk i-1 downloads.
 // commit(fuse=1) rewrites adjacent blocks into fused kernels:
-//   Rotator -> FIR(crcf) -> Downsampler   =>  tuner kernel      (composites/tuner.lua:40-47)
+//   Rotator -> FIR(crcf) -> Downsampler [-> Discriminator]  =>  tuner kernel (composites/tuner.lua:40-47)
 //   FIR -> Downsampler                    =>  decimating FIR    (composites/decimator.lua:34-41)
 //   IIR -> Downsampler                    =>  scan with strided store
 #include "../../include/lrb200.h"
@@ -81,8 +81,9 @@ struct Graph {
                     FirBlock* f2 = dynamic_cast<FirBlock*>(blocks[i + 1]);
                     DownsampleBlock* d3 = dynamic_cast<DownsampleBlock*>(blocks[i + 2]);
                     if (f2 && d3 && f2->kind == FIR_CRCF && f2->D == 1 && d3->in_size == 8) {
-                        Block* t = make_tuner(rot->turns, (const float*)f2->h_taps.data(), f2->M, d3->D);
-                        if (t) { fused.push_back(t); st = t; used = 3; }
+                        DiscrimBlock* d4 = (i + 3 < blocks.size()) ? dynamic_cast<DiscrimBlock*>(blocks[i + 3]) : nullptr;
+                        Block* t = make_tuner(rot->turns, (const float*)f2->h_taps.data(), f2->M, d3->D, d4 ? d4->gain : 0.0f);
+                        if (t) { fused.push_back(t); st = t; used = d4 ? 4 : 3; }
                     }
                 }
                 if (used == 1 && fir && fir->D == 1 && fir->kind != FIR_HILBERT && i + 1 < blocks.size()) {

@@ -9,6 +9,7 @@
 //   grid:   decoupled look-back over per-tile (aggregate | inclusive prefix) records.
 // The input is read once and the output written once (8 B/sample real, 16 B/sample complex).
 #include "common.cuh"
+#include <cmath>
 
 namespace lrb {
 
@@ -45,7 +46,14 @@ __device__ __forceinline__ float2 add_t(float2 a, float2 b) { return __fadd2_rn(
 __device__ __forceinline__ float ld_cg(const float* p) { return __ldcg(p); }
 __device__ __forceinline__ float2 ld_cg(const float2* p) { return __ldcg(p); }
 
-template <typename T>
+// LOCAL = true: the pole's memory is shorter than IIR_WARM samples (|c|^IIR_WARM < 1e-12, e.g. FM de-emphasis
+// at 220.5 kHz: 0.9413^512 = 4e-14), so a tile needs nothing from its predecessors beyond float32 resolution:
+// every CTA restarts IIR_WARM samples early from a zero state and discards that lead-in.  No tickets, flags or
+// fences -- a plain streaming kernel.  LOCAL = false: exact decoupled look-back for slow poles.
+constexpr int IIR_WARM = 512;
+constexpr int IIR_PAY = IIR_THREADS * IIR_V - IIR_WARM;   // payload samples per CTA after the first
+
+template <typename T, bool LOCAL>
 __global__ void __launch_bounds__(IIR_THREADS)
 iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirParams P,
                  const T* __restrict__ xhist_in, T* __restrict__ xhist_out,
@@ -55,10 +63,20 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     __shared__ T s_warp[IIR_THREADS / 32];
     __shared__ T s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(ticket, 1);
-    __syncthreads();
-    const int tile = s_tile;
-    const long long base = (long long)tile * IIR_TILE + (long long)tid * IIR_V;
+    int tile;
+    long long span0;                                  // first sample index of this CTA's span
+    long long pay0;                                   // first sample index this CTA stores
+    if constexpr (LOCAL) {
+        tile = blockIdx.x;
+        pay0 = tile == 0 ? 0 : (long long)IIR_TILE + (long long)(tile - 1) * IIR_PAY;
+        span0 = tile == 0 ? 0 : pay0 - IIR_WARM;
+    } else {
+        if (tid == 0) s_tile = atomicAdd(ticket, 1);
+        __syncthreads();
+        tile = s_tile;
+        span0 = pay0 = (long long)tile * IIR_TILE;
+    }
+    const long long base = span0 + (long long)tid * IIR_V;
     const int nh = P.nb - 1;
 
     // ---- u[i] = sum_j b[j] x[i-j] over this thread's V samples (zero beyond n)
@@ -106,7 +124,9 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     __shared__ T s_agg;
     if (tid == IIR_THREADS - 1) s_agg = fmas(f_lane * P.cp[0], carryW, B);
     __syncthreads();
-    if (warp == 0) {
+    if constexpr (LOCAL) {
+        if (tid == 0) s_carry = (tile == 0) ? __ldg(ystate_in) : zero_of(T());
+    } else if (warp == 0) {
         const float cT = P.cp[5 + IIR_LOGW];
         T carry_in;
         if (tile == 0) {
@@ -163,20 +183,38 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     for (int k = 0; k < IIR_LOGW; ++k) if (warp & (1 << k)) f_thread *= P.cp[5 + k];
     const T carry_t = fmas(f_thread, carry_in, excl);
 
-    // ---- outputs y[i] = yl[i] + c^(i+1) * carry_t
+    // ---- outputs y[i] = yl[i] + c^(i+1) * carry_t.  Fused decimation keeps sample idx when (idx - first) % D == 0;
+    // the residue/quotient are tracked incrementally from one 32-bit division per thread (a 64-bit division per
+    // sample made the first version instruction-bound: 140 instructions per sample in ncu).
+    int res = 0;
+    long long jout = 0;
+    if (D > 1) {
+        const long long d0 = base - first;
+        if (d0 >= 0) {
+            const unsigned q = (unsigned)d0 / (unsigned)D;
+            res = (int)((unsigned)d0 - q * (unsigned)D);
+            jout = (long long)q + (res ? 1 : 0);          // index of the next kept sample
+            res = res ? res - D : 0;                      // res <= 0: samples until the next kept one (negated)
+        } else {
+            res = (int)d0;                                // before the first kept sample
+        }
+    }
     float cpow = P.c;
 #pragma unroll
     for (int i = 0; i < IIR_V; ++i) {
         long long idx = base + i;
         T v = fmas(cpow, carry_t, yl[i]);
         cpow *= P.c;
-        if (idx < n) {
+        if (idx < n && idx >= pay0) {
             if (D == 1) {
                 y[idx] = v;
-            } else if (idx >= first && ((idx - first) % D) == 0) {
-                y[(idx - first) / D] = v;
+            } else if (res == 0) {
+                y[jout] = v;
             }
             if (idx == n - 1) *ystate_out = v;
+        }
+        if (D > 1) {
+            if (res == 0) { res = 1 - D; ++jout; } else { ++res; }
         }
     }
     // ---- carried input history for the next call: last nb-1 inputs of [xhist_in | x]
@@ -219,6 +257,21 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
     double cd = (double)c, p = 1.0;
     for (int i = 0; i < IIR_V; ++i) p *= cd;      // c^V
     for (int k = 0; k < 5 + IIR_LOGW + 1; ++k) { P.cp[k] = (float)p; p = p * p; }
+    const bool local = std::pow(std::fabs(cd), (double)IIR_WARM) < 1e-12;
+    if (local) {
+        int tiles = n <= IIR_TILE ? 1 : 1 + (int)((n - IIR_TILE + IIR_PAY - 1) / IIR_PAY);
+        if (complex_data)
+            iir1_scan_kernel<float2, true><<<tiles, IIR_THREADS, 0, s>>>((const float2*)x, n, (float2*)y, P,
+                (const float2*)xhist_in, (float2*)xhist_out, (const float2*)ystate_in, (float2*)ystate_out,
+                first, D, nullptr, nullptr, nullptr, nullptr, 0u);
+        else
+            iir1_scan_kernel<float, true><<<tiles, IIR_THREADS, 0, s>>>((const float*)x, n, (float*)y, P,
+                (const float*)xhist_in, (float*)xhist_out, (const float*)ystate_in, (float*)ystate_out,
+                first, D, nullptr, nullptr, nullptr, nullptr, 0u);
+        count_launch();
+        LRB_CHECK(cudaGetLastError());
+        return 0;
+    }
     w->epoch = (w->epoch + 1) & 0x3fffffffu;
     if (w->epoch == 0) {                          // wrapped: clear stale flags
         LRB_CHECK(cudaMemsetAsync(w->flags, 0, sizeof(int) * w->max_tiles, s));
@@ -227,11 +280,11 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
     LRB_CHECK(cudaMemsetAsync(w->ticket, 0, sizeof(int), s));
     int tiles = (int)((n + IIR_TILE - 1) / IIR_TILE);
     if (complex_data)
-        iir1_scan_kernel<float2><<<tiles, IIR_THREADS, 0, s>>>((const float2*)x, n, (float2*)y, P,
+        iir1_scan_kernel<float2, false><<<tiles, IIR_THREADS, 0, s>>>((const float2*)x, n, (float2*)y, P,
             (const float2*)xhist_in, (float2*)xhist_out, (const float2*)ystate_in, (float2*)ystate_out,
             first, D, w->ticket, w->flags, (float2*)w->agg, (float2*)w->pfx, w->epoch);
     else
-        iir1_scan_kernel<float><<<tiles, IIR_THREADS, 0, s>>>((const float*)x, n, (float*)y, P,
+        iir1_scan_kernel<float, false><<<tiles, IIR_THREADS, 0, s>>>((const float*)x, n, (float*)y, P,
             (const float*)xhist_in, (float*)xhist_out, (const float*)ystate_in, (float*)ystate_out,
             first, D, w->ticket, w->flags, (float*)w->agg, (float*)w->pfx, w->epoch);
     count_launch();
