@@ -39,10 +39,14 @@ struct FirBlock : Block {
     void* d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     int algo = 0;                     // LRB200_FIR_AUTO / DIRECT / FFT
+    bool rotate = false;              // fused FrequencyTranslator in front (graph fusion; FFT path only)
+    double rot_turns = 0.0;
+    uint64_t rot_fix = 0;
     FirFast* fast = nullptr;
     PolyTaps* poly = nullptr;
 
     FirBlock(FirKind k, const void* taps_host, unsigned ntaps, unsigned decim, bool dev);
+    void set_rotation(double turns_per_sample) { rotate = true; rot_turns = turns_per_sample; rot_fix = turns_to_fix(turns_per_sample); }
     ~FirBlock() override;
     int init() override;
     size_t max_output(size_t n) const override;

@@ -47,35 +47,68 @@ __device__ __forceinline__ float2 cmul_conj_if(float2 a, float2 w, bool conj) {
     return __ffma2_rn(a, make_float2(w.x, w.x), t);
 }
 
-// MODE 0: complex input / complex output (crcf, cccf).  MODE 1: real input packed two blocks per FFT (rrrf).
-// EDGE false: interior blocks [b_lo, b_hi) whose N inputs and L outputs all lie inside x / y: unconditional,
-//             fully coalesced loads and stores, one code path (the compiler otherwise clones the butterfly
-//             networks behind each branch of a guarded load).
-// EDGE true : the few blocks that touch the carried history (b = 0) or the end of the input (b >= b_hi):
-//             edge index e = 0 -> block 0, e >= 1 -> block b_hi + e - 1; every access is bounds-checked.
-template <int MODE, bool EDGE>
+struct FftArgs {
+    const void* x;
+    const void* hist;
+    void* y;
+    const float2* H;          // [k2][k1] tap spectrum / N
+    const float2* tw;         // [a][b] W1024^(a*b)
+    const float2* E;          // [r][lane] exp(j*2*pi*turns*(32 r + lane))  (ROT only)
+    long long n;
+    long long b_lo, b_hi, nwork;
+    long long first;          // decimation: keep outputs at input index first + j*D
+    uint64_t turns_fix, g0;   // fused translator
+    int M, D;
+};
+
+// floor division helpers for (possibly negative) t and positive d
+__device__ __forceinline__ void floor_divmod(long long t, int d, long long* q, int* r) {
+    long long qq = t / d;
+    long long rr = t - qq * d;
+    if (rr < 0) { rr += d; qq -= 1; }
+    *q = qq;
+    *r = (int)rr;
+}
+
+// IN   0: complex in / complex out (crcf, cccf)         1: real in, two blocks packed per FFT / real out (rrrf)
+//      2: real in / complex out with complex taps (Hilbert: taps = delay + j*hilbert)
+// EDGE false: interior blocks [b_lo, b_hi): all N inputs inside x, unconditional coalesced loads (one code path:
+//             guarded loads made the compiler clone the butterfly networks behind each branch);
+//      true : blocks touching the carried history (b = 0) or the end of the input (b >= b_hi), bounds-checked;
+//             work index e = 0 -> block 0, e >= 1 -> block b_hi + e - 1.
+// ROT  (IN 0): fused FrequencyTranslator: x[i] * exp(j w (g0+i)) = P_b * (x[i] * E[i - base]); E is applied at the
+//             load, the per-block phasor P_b commutes with the (linear) filter and is applied to kept outputs only.
+// DEC  fused Downsampler: only outputs at input index first + j*D are stored, at y[j].
+template <int IN, bool EDGE, bool ROT, bool DEC>
 __global__ void __launch_bounds__(FF_THREADS, 2)
-fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, long long n, void* __restrict__ yv,
-                   const float2* __restrict__ Hg, const float2* __restrict__ twg, int M, long long b_lo, long long b_hi,
-                   long long nwork) {
+fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
     extern __shared__ __align__(16) float2 sm[];
     float2* s_tw = sm;                            // [k1][n2]  W1024^(k1*n2)
     float2* s_H = sm + FF_N;                      // [k2][k1]  H[k1 + 32 k2] / N
+    float2* s_E = sm + 2 * FF_N;                  // [r][lane] (ROT)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float2* xch = sm + 2 * FF_N + warp * FF_XCH;
-    for (int i = tid; i < FF_N; i += FF_THREADS) { s_tw[i] = twg[i]; s_H[i] = Hg[i]; }
+    float2* xch = sm + (ROT ? 3 : 2) * FF_N + warp * FF_XCH;
+    for (int i = tid; i < FF_N; i += FF_THREADS) {
+        s_tw[i] = A.tw[i];
+        s_H[i] = A.H[i];
+        if constexpr (ROT) s_E[i] = A.E[i];
+    }
     __syncthreads();
 
+    const int M = A.M;
+    const long long n = A.n;
     const int L = FF_N - (M - 1);
     const int Hm1 = M - 1;
+    const int D = A.D;
+    const int s32 = DEC ? 32 % D : 0, q32 = DEC ? 32 / D : 0;
     const long long wstride = (long long)gridDim.x * FF_WARPS;
-    for (long long wi = (long long)blockIdx.x * FF_WARPS + warp; wi < nwork; wi += wstride) {
-        const long long b = EDGE ? (wi == 0 ? 0 : b_hi + wi - 1) : (b_lo + wi);
+    for (long long wi = (long long)blockIdx.x * FF_WARPS + warp; wi < A.nwork; wi += wstride) {
+        const long long b = EDGE ? (wi == 0 ? 0 : A.b_hi + wi - 1) : (A.b_lo + wi);
         float2 v[32];
         // ---- load: v[r] = X[base + 32 r + lane]
-        if constexpr (MODE == 0) {
-            const float2* x = reinterpret_cast<const float2*>(xv);
-            const float2* hist = reinterpret_cast<const float2*>(histv);
+        if constexpr (IN == 0) {
+            const float2* x = reinterpret_cast<const float2*>(A.x);
+            const float2* hist = reinterpret_cast<const float2*>(A.hist);
             const long long base = b * L - Hm1;
             if constexpr (!EDGE) {
                 const float2* xb = x + base + lane;
@@ -88,10 +121,14 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
                     v[r] = (i >= 0) ? (i < n ? __ldg(x + i) : make_float2(0.f, 0.f)) : __ldg(hist + (Hm1 + i));
                 }
             }
-        } else {
+            if constexpr (ROT) {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = cmul_conj_if(v[r], s_E[r * 32 + lane], false);
+            }
+        } else if constexpr (IN == 1) {
             // two consecutive real blocks 2b, 2b+1 as real / imaginary part
-            const float* x = reinterpret_cast<const float*>(xv);
-            const float* hist = reinterpret_cast<const float*>(histv);
+            const float* x = reinterpret_cast<const float*>(A.x);
+            const float* hist = reinterpret_cast<const float*>(A.hist);
             const long long base0 = (2 * b) * L - Hm1, base1 = base0 + L;
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
@@ -103,6 +140,18 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
                     const float c = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : 0.f) : __ldg(hist + (Hm1 + i1));
                     v[r] = make_float2(a, c);
                 }
+            }
+        } else {
+            const float* x = reinterpret_cast<const float*>(A.x);
+            const float* hist = reinterpret_cast<const float*>(A.hist);
+            const long long base = b * L - Hm1;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const long long i = base + 32 * r + lane;
+                float a;
+                if constexpr (!EDGE) a = __ldcs(x + i);
+                else a = (i >= 0) ? (i < n ? __ldg(x + i) : 0.f) : __ldg(hist + (Hm1 + i));
+                v[r] = make_float2(a, 0.f);
             }
         }
 
@@ -138,30 +187,99 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
         // ---- inverse pass 2: registers k1 -> n1 (y[n2 + 32 n1] in v[bitrev5(n1)])
         fft32_nat2br<true>(v);
 
-        // ---- store the L valid outputs: block index n = 32 n1 + lane >= M-1  ->  y[b L + n - (M-1)]
-        if constexpr (MODE == 0) {
-            float2* y = reinterpret_cast<float2*>(yv);
+        // ---- store the L valid outputs: block index nn = 32 n1 + lane >= M-1  ->  input-aligned index o = obase + nn
+        if constexpr (IN == 0 || IN == 2) {
+            float2* y = reinterpret_cast<float2*>(A.y);
             const long long obase = b * L - Hm1;
+            if constexpr (!DEC) {
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {
-                const int nn = 32 * n1 + lane;
-                const long long o = obase + nn;
-                if (nn >= Hm1 && (!EDGE || o < n)) __stcs(y + o, v[bitrev5(n1)]);
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const int nn = 32 * n1 + lane;
+                    const long long o = obase + nn;
+                    if (nn >= Hm1 && (!EDGE || o < n)) __stcs(y + o, v[bitrev5(n1)]);
+                }
+            } else {
+                float2 Pb = make_float2(1.f, 0.f);
+                if constexpr (ROT) Pb = phasor_from_fix(A.turns_fix * (A.g0 + (uint64_t)obase));
+                long long q;
+                int r;
+                floor_divmod(obase + lane - A.first, D, &q, &r);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const int nn = 32 * n1 + lane;
+                    if (r == 0 && q >= 0 && nn >= Hm1 && (!EDGE || obase + nn < n)) {
+                        float2 t = v[bitrev5(n1)];
+                        if constexpr (ROT) t = cmul_conj_if(t, Pb, false);
+                        y[q] = t;
+                    }
+                    r += s32;
+                    q += q32;
+                    if (r >= D) { r -= D; ++q; }
+                }
             }
         } else {
-            float* y = reinterpret_cast<float*>(yv);
+            float* y = reinterpret_cast<float*>(A.y);
             const long long obase0 = (2 * b) * L - Hm1, obase1 = obase0 + L;
+            if constexpr (!DEC) {
 #pragma unroll
-            for (int n1 = 0; n1 < 32; ++n1) {
-                const int nn = 32 * n1 + lane;
-                if (nn >= Hm1) {
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const int nn = 32 * n1 + lane;
+                    if (nn >= Hm1) {
+                        const float2 t = v[bitrev5(n1)];
+                        if (!EDGE || obase0 + nn < n) y[obase0 + nn] = t.x;
+                        if (!EDGE || obase1 + nn < n) y[obase1 + nn] = t.y;
+                    }
+                }
+            } else {
+                long long q0, q1;
+                int r0, r1;
+                floor_divmod(obase0 + lane - A.first, D, &q0, &r0);
+                floor_divmod(obase1 + lane - A.first, D, &q1, &r1);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const int nn = 32 * n1 + lane;
                     const float2 t = v[bitrev5(n1)];
-                    if (!EDGE || obase0 + nn < n) y[obase0 + nn] = t.x;
-                    if (!EDGE || obase1 + nn < n) y[obase1 + nn] = t.y;
+                    if (nn >= Hm1) {
+                        if (r0 == 0 && q0 >= 0 && (!EDGE || obase0 + nn < n)) y[q0] = t.x;
+                        if (r1 == 0 && q1 >= 0 && (!EDGE || obase1 + nn < n)) y[q1] = t.y;
+                    }
+                    r0 += s32; q0 += q32; if (r0 >= D) { r0 -= D; ++q0; }
+                    r1 += s32; q1 += q32; if (r1 >= D) { r1 -= D; ++q1; }
                 }
             }
         }
     }
+}
+
+template <int IN, bool ROT, bool DEC>
+int launch_fft(const FftArgs& base_args, long long n_int, long long n_edge, cudaStream_t s) {
+    static bool configured = false;
+    constexpr size_t smem = (size_t)((ROT ? 3 : 2) * FF_N + FF_WARPS * FF_XCH) * sizeof(float2);
+    auto ki = fir_fft1024_kernel<IN, false, ROT, DEC>;
+    auto ke = fir_fft1024_kernel<IN, true, ROT, DEC>;
+    if (!configured) {
+        LRB_CHECK(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LRB_CHECK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long max_ctas = (long long)ctx().sm_count * 2;
+    if (n_int > 0) {
+        FftArgs a = base_args;
+        a.nwork = n_int;
+        long long ctas = (n_int + FF_WARPS - 1) / FF_WARPS;
+        if (ctas > max_ctas) ctas = max_ctas;
+        ki<<<(unsigned)ctas, FF_THREADS, smem, s>>>(a);
+        count_launch();
+    }
+    if (n_edge > 0) {
+        FftArgs a = base_args;
+        a.nwork = n_edge;
+        long long ctas = (n_edge + FF_WARPS - 1) / FF_WARPS;
+        ke<<<(unsigned)ctas, FF_THREADS, smem, s>>>(a);
+        count_launch();
+    }
+    LRB_CHECK(cudaGetLastError());
+    return 1;
 }
 
 }  // namespace
@@ -173,25 +291,28 @@ fir_fft1024_kernel(const void* __restrict__ xv, const void* __restrict__ histv, 
 struct FirFast {
     float2* d_H = nullptr;
     float2* d_tw = nullptr;
-    int mode = 0;
-    bool configured = false;
+    float2* d_E = nullptr;
+    int in_mode = 0;
 };
 
 static constexpr int FFT_MAX_TAPS = 513;       // L >= 512: at most half of every block is overlap
 
 int FirBlock::fast_init() {
-    if (kind == FIR_CRCF && D > 1) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
-    if (D != 1 || kind == FIR_HILBERT || M > FFT_MAX_TAPS) return 0;
+    if (kind == FIR_CRCF && D > 1 && !rotate) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
+    if (M > FFT_MAX_TAPS) return 0;
+    if (kind == FIR_HILBERT && D != 1) return 0;
     fast = new (std::nothrow) FirFast();
     if (!fast) { set_error("out of memory"); return -1; }
-    fast->mode = (kind == FIR_RRRF) ? 1 : 0;
+    fast->in_mode = (kind == FIR_RRRF) ? 1 : (kind == FIR_HILBERT ? 2 : 0);
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<std::complex<double>> h(M);
+    const float* tf = (const float*)h_taps.data();
     for (int k = 0; k < M; ++k) {
-        if (kind == FIR_CCCF) h[k] = std::complex<double>(((const float*)h_taps.data())[2 * k], ((const float*)h_taps.data())[2 * k + 1]);
-        else h[k] = std::complex<double>(((const float*)h_taps.data())[k], 0.0);
+        if (kind == FIR_CCCF) h[k] = std::complex<double>(tf[2 * k], tf[2 * k + 1]);
+        else if (kind == FIR_HILBERT) h[k] = std::complex<double>(k == (M - 1) / 2 ? 1.0 : 0.0, tf[k]);   // delay + j*hilbert (hilberttransform.lua:120-124)
+        else h[k] = std::complex<double>(tf[k], 0.0);
     }
-    std::vector<float2> H(FF_N), tw(FF_N);
+    std::vector<float2> H(FF_N), tw(FF_N), E(FF_N);
     for (int k = 0; k < FF_N; ++k) {
         std::complex<double> acc(0.0, 0.0);
         for (int m = 0; m < M; ++m) {
@@ -211,6 +332,17 @@ int FirBlock::fast_init() {
     LRB_CHECK(cudaMalloc(&fast->d_tw, sizeof(float2) * FF_N));
     LRB_CHECK(cudaMemcpy(fast->d_H, H.data(), sizeof(float2) * FF_N, cudaMemcpyHostToDevice));
     LRB_CHECK(cudaMemcpy(fast->d_tw, tw.data(), sizeof(float2) * FF_N, cudaMemcpyHostToDevice));
+    if (rotate) {
+        // E[n] = exp(j 2 pi turns n) from the same 2^-64 fixed-point turns the kernel uses for the block phasor
+        const long double tq = ldexpl((long double)rot_fix, -64);
+        for (int i = 0; i < FF_N; ++i) {
+            long double a = tq * (long double)i;
+            a -= floorl(a);
+            E[i] = make_float2((float)std::cos(two_pi * (double)a), (float)std::sin(two_pi * (double)a));
+        }
+        LRB_CHECK(cudaMalloc(&fast->d_E, sizeof(float2) * FF_N));
+        LRB_CHECK(cudaMemcpy(fast->d_E, E.data(), sizeof(float2) * FF_N, cudaMemcpyHostToDevice));
+    }
     return 0;
 }
 
@@ -220,6 +352,7 @@ void FirBlock::fast_free() {
     if (fast) {
         cudaFree(fast->d_H);
         cudaFree(fast->d_tw);
+        cudaFree(fast->d_E);
         delete fast;
         fast = nullptr;
     }
@@ -227,13 +360,17 @@ void FirBlock::fast_free() {
 
 // The algorithm that would run for a long input (what lrb200_fir_get_algorithm reports).
 int FirBlock::effective_algorithm() const {
+    if (rotate) return LRB200_FIR_FFT;                         // the fused translator exists only in the FFT kernel
     if (!fast || algo == LRB200_FIR_DIRECT) return LRB200_FIR_DIRECT;
     if (algo == LRB200_FIR_FFT) return LRB200_FIR_FFT;
-    // automatic: overlap-save once the direct form would be FP32-bound.  Packed FFMA2 per sample:
-    // direct = M (crcf), 2M (cccf), M/2 (rrrf);  overlap-save ~ 31 / (L/N) (half for packed real blocks)
-    const int direct_cost = kind == FIR_CCCF ? 2 * M : kind == FIR_RRRF ? (M + 1) / 2 : M;
+    if (poly) return LRB200_FIR_DIRECT;                        // register-tiled polyphase decimator
+    // automatic: overlap-save once the direct form would be FP32-bound.  Packed FFMA2 per INPUT sample:
+    //   direct = M/D (crcf), 2M/D (cccf), M/2D (rrrf, hilbert);  overlap-save ~ 31 / (L/N) (half for packed real blocks)
+    // The only direct kernel for these shapes is the catch-all (about 8x off its FP32 bound), hence the factor.
+    const double per_tap = kind == FIR_CCCF ? 2.0 : (kind == FIR_CRCF ? 1.0 : 0.5);
+    const double direct_cost = 8.0 * per_tap * M / D;
     const double fft_cost = 31.0 * FF_N / (double)(FF_N - M + 1) * (kind == FIR_RRRF ? 0.5 : 1.0);
-    return (double)direct_cost > 1.15 * fft_cost ? LRB200_FIR_FFT : LRB200_FIR_DIRECT;
+    return direct_cost > fft_cost ? LRB200_FIR_FFT : LRB200_FIR_DIRECT;
 }
 
 int FirBlock::set_algorithm(int a) {
@@ -243,47 +380,37 @@ int FirBlock::set_algorithm(int a) {
 }
 
 int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long long n_out, cudaStream_t s) {
-    if (poly && D > 1)
+    if (poly && D > 1 && algo != LRB200_FIR_FFT)
         return launch_polyphase_crcf(poly, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, (float2*)dy,
                                      first, n_out, false, 0, consumed, s);
-    if (!fast || effective_algorithm() != LRB200_FIR_FFT) return 0;
+    if (!fast || effective_algorithm() != LRB200_FIR_FFT) {
+        if (rotate) { set_error("fir: fused translator needs the overlap-save path (ntaps <= %d)", FFT_MAX_TAPS); return -1; }
+        return 0;
+    }
     const int L = FF_N - (M - 1);
-    // a forced FFT always runs; the automatic choice leaves short calls (a few blocks) to the direct kernel
-    if (algo != LRB200_FIR_FFT && (long long)n < 8LL * L) return 0;
+    // a forced FFT (or a fused translator) always runs; the automatic choice leaves short calls to the direct kernel
+    if (algo != LRB200_FIR_FFT && !rotate && (long long)n < 8LL * L) return 0;
     // blocks of L outputs; in packed-real mode one FFT covers two of them
-    const long long per = (fast->mode == 1) ? 2LL * L : (long long)L;
+    const long long per = (fast->in_mode == 1) ? 2LL * L : (long long)L;
     const long long nblocks = ((long long)n + per - 1) / per;
     long long b_hi = (long long)n / per;                 // blocks [1, b_hi) are interior
     if (b_hi < 1) b_hi = 1;
     if (b_hi > nblocks) b_hi = nblocks;
+    FftArgs a;
+    a.x = dx; a.hist = d_hist[cur]; a.y = dy; a.H = fast->d_H; a.tw = fast->d_tw; a.E = fast->d_E;
+    a.n = (long long)n; a.b_lo = 1; a.b_hi = b_hi; a.nwork = 0; a.first = first;
+    a.turns_fix = rot_fix; a.g0 = consumed; a.M = M; a.D = D;
     const long long n_int = b_hi - 1, n_edge = 1 + (nblocks - b_hi);
-    if (!fast->configured) {
-        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
-        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
-        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
-        LRB_CHECK(cudaFuncSetAttribute(fir_fft1024_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FF_SMEM));
-        fast->configured = true;
+    const bool dec = D > 1;
+    switch (fast->in_mode) {
+        case 0:
+            if (rotate) return launch_fft<0, true, true>(a, n_int, n_edge, s);       // fused translator always uses the DEC store (D may be 1)
+            return dec ? launch_fft<0, false, true>(a, n_int, n_edge, s) : launch_fft<0, false, false>(a, n_int, n_edge, s);
+        case 1:
+            return dec ? launch_fft<1, false, true>(a, n_int, n_edge, s) : launch_fft<1, false, false>(a, n_int, n_edge, s);
+        default:
+            return launch_fft<2, false, false>(a, n_int, n_edge, s);
     }
-    const long long max_ctas = (long long)ctx().sm_count * 2;
-    if (n_int > 0) {
-        long long ctas = (n_int + FF_WARPS - 1) / FF_WARPS;
-        if (ctas > max_ctas) ctas = max_ctas;
-        if (fast->mode == 0)
-            fir_fft1024_kernel<0, false><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_int);
-        else
-            fir_fft1024_kernel<1, false><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_int);
-        count_launch();
-    }
-    {
-        long long ctas = (n_edge + FF_WARPS - 1) / FF_WARPS;
-        if (fast->mode == 0)
-            fir_fft1024_kernel<0, true><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_edge);
-        else
-            fir_fft1024_kernel<1, true><<<(unsigned)ctas, FF_THREADS, FF_SMEM, s>>>(dx, d_hist[cur], (long long)n, dy, fast->d_H, fast->d_tw, M, 1, b_hi, n_edge);
-        count_launch();
-    }
-    LRB_CHECK(cudaGetLastError());
-    return 1;
 }
 
 }  // namespace lrb

@@ -77,13 +77,24 @@ struct Graph {
                 RotatorBlock* rot = dynamic_cast<RotatorBlock*>(b);
                 FirBlock* fir = dynamic_cast<FirBlock*>(b);
                 IirBlock* iir = dynamic_cast<IirBlock*>(b);
-                if (rot && i + 2 < blocks.size()) {
+                if (rot && i + 1 < blocks.size()) {
                     FirBlock* f2 = dynamic_cast<FirBlock*>(blocks[i + 1]);
-                    DownsampleBlock* d3 = dynamic_cast<DownsampleBlock*>(blocks[i + 2]);
-                    if (f2 && d3 && f2->kind == FIR_CRCF && f2->D == 1 && d3->in_size == 8) {
+                    DownsampleBlock* d3 = (i + 2 < blocks.size()) ? dynamic_cast<DownsampleBlock*>(blocks[i + 2]) : nullptr;
+                    if (d3 && d3->in_size != 8) d3 = nullptr;
+                    const bool fir_ok = f2 && (f2->kind == FIR_CRCF || f2->kind == FIR_CCCF) && f2->D == 1;
+                    if (fir_ok && d3 && f2->kind == FIR_CRCF) {
                         DiscrimBlock* d4 = (i + 3 < blocks.size()) ? dynamic_cast<DiscrimBlock*>(blocks[i + 3]) : nullptr;
                         Block* t = make_tuner(rot->turns, (const float*)f2->h_taps.data(), f2->M, d3->D, d4 ? d4->gain : 0.0f);
                         if (t) { fused.push_back(t); st = t; used = d4 ? 4 : 3; }
+                    }
+                    if (used == 1 && fir_ok && f2->M <= 513) {
+                        // translator folded into the overlap-save kernel (any taps, complex taps included)
+                        FirBlock* nf = new (std::nothrow) FirBlock(f2->kind, f2->h_taps.data(), (unsigned)f2->M, (unsigned)(d3 ? d3->D : 1), true);
+                        if (!nf) { set_error("out of memory"); return -1; }
+                        nf->set_rotation(rot->turns);
+                        nf->name = f2->kind == FIR_CCCF ? "rot+fir_cccf" : "rot+fir_crcf";
+                        if (nf->init() != 0) { delete nf; return -1; }
+                        fused.push_back(nf); st = nf; used = d3 ? 3 : 2;
                     }
                 }
                 if (used == 1 && fir && fir->D == 1 && fir->kind != FIR_HILBERT && i + 1 < blocks.size()) {

@@ -196,3 +196,92 @@ def test_wbfm_mono_chain(fuse, chunk):
         assert "tuner" in top.describe_gpu_graph()
     # the demodulated tone must be there (sanity that the chain does FM demodulation, not just agreement)
     assert np.max(np.abs(ref[2000:])) > 0.05
+
+
+@pytest.mark.parametrize("kind", ["crcf", "cccf", "rrrf"])
+@pytest.mark.parametrize("D,M", [(5, 128), (7, 200), (3, 33), (25, 513), (2, 16)])
+@pytest.mark.parametrize("algo", [_lib.FIR_AUTO, _lib.FIR_DIRECT, _lib.FIR_FFT])
+def test_decimating_fir_all_kinds_and_algorithms(kind, D, M, algo):
+    """C-ABI `decim` for every type combination and both algorithms == FIR -> Downsampler of the oracle."""
+    rng = np.random.default_rng(D * 1000 + M + len(kind))
+    n = 120000
+    taps = O.firwin_lowpass(M, 1.0 / D)
+    if kind == "cccf":
+        taps = taps * np.exp(1j * 0.3 * np.arange(M))
+    taps = O.f32_taps(taps)
+    x = rng.uniform(-1, 1, n).astype(np.float32) if kind == "rrrf" else rnd_c(rng, n)
+    lib = _lib.require_device()
+    create = {"crcf": lib.lrb200_fir_create_crcf, "cccf": lib.lrb200_fir_create_cccf, "rrrf": lib.lrb200_fir_create_rrrf}[kind]
+    h = _lib.check_handle(create(taps.ctypes.data, M, D, _lib.LRB200_HOST), "fir")
+    _lib.check(lib.lrb200_fir_set_algorithm(h, algo))
+    outs = []
+    for a, b in ragged(rng, n, 0, 60000):
+        seg = np.ascontiguousarray(x[a:b])
+        out = np.zeros(lib.lrb200_block_max_output(h, len(seg)), x.dtype)
+        no = ctypes.c_size_t()
+        _lib.check(lib.lrb200_fir_execute(h, seg.ctypes.data, len(seg), out.ctypes.data, ctypes.byref(no)))
+        outs.append(out[:no.value])
+    lib.lrb200_fir_destroy(h)
+    ref = O.Chain(O.FIRFilter(taps, kind != "rrrf"), O.Downsampler(D)).process(x)
+    close(np.concatenate(outs), ref)
+
+
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("D", [1, 5])
+def test_translator_complex_fir_decimate_graph(fuse, D):
+    """BASELINE config 1 shape: FrequencyTranslator -> 128-tap COMPLEX-tap FIR -> /5, as a flow graph
+    (fused: translator folded into the overlap-save kernel) vs the oracle."""
+    rate, n = 1102500.0, 700000
+    rng = np.random.default_rng(77)
+    x = O.synth_white_iq(0, n)
+    blocks = [radio.FrequencyTranslatorBlock(-250e3), radio.ComplexBandpassFilterBlock(128, [-100e3, 100e3])]
+    if D > 1:
+        blocks.append(radio.DownsamplerBlock(D))
+    src, snk = radio.ArraySource(x, rate, 250001), radio.ArraySink()
+    top = radio.CompositeBlock()
+    top.connect(src, *blocks, snk)
+    top.run(False, fuse=fuse)
+    ochain = [O.FrequencyTranslator(-250e3, rate), O.complex_bandpass_filter(128, [-100e3, 100e3], rate)]
+    if D > 1:
+        ochain.append(O.Downsampler(D))
+    close(snk.result(), O.Chain(*ochain).process(x))
+    if fuse:
+        assert "rot+fir_cccf" in top.describe_gpu_graph(), top.describe_gpu_graph()
+
+
+def test_hilbert_long_call_uses_fft_path():
+    rng = np.random.default_rng(10)
+    n = 200000
+    xr = rng.uniform(-1, 1, n).astype(np.float32)
+    for M in (65, 129, 257):
+        blk = mk(radio.HilbertTransformBlock, [M], Float32)
+        got = np.concatenate([np.array(blk.process(Vector.cast(xr[:150000])).data, copy=True),
+                              np.array(blk.process(Vector.cast(xr[150000:])).data, copy=True)])
+        close(got, O.HilbertTransform(M).process(xr))
+
+
+def test_c_abi_argument_errors():
+    lib = _lib.require_device()
+    taps = np.ones(4, np.float32)
+    assert not lib.lrb200_fir_create_crcf(None, 4, 1, 0)
+    assert not lib.lrb200_fir_create_crcf(taps.ctypes.data, 0, 1, 0)
+    assert not lib.lrb200_fir_create_crcf(taps.ctypes.data, 4, 0, 0)
+    assert b"decimation" in lib.lrb200_last_error()
+    assert not lib.lrb200_hilbert_create(taps.ctypes.data, 4, 0)          # even tap count
+    assert not lib.lrb200_downsample_create(0, 8, 0)
+    assert not lib.lrb200_downsample_create(2, 3, 0)
+    assert not lib.lrb200_discrim_create(0.0, 0)
+    assert lib.lrb200_block_execute(None, None, 0, None, None) != 0
+    h = lib.lrb200_fir_create_crcf(taps.ctypes.data, 4, 1, 0)
+    assert h and lib.lrb200_fir_set_algorithm(h, 7) != 0
+    assert lib.lrb200_block_execute(h, None, 5, None, None) != 0          # null buffers with n > 0
+    lib.lrb200_fir_destroy(h)
+    g = lib.lrb200_graph_create()
+    hh = lib.lrb200_cmag_create(_lib.LRB200_HOST)
+    assert lib.lrb200_graph_append(g, hh) != 0                            # host-mode block in a device graph
+    lib.lrb200_block_destroy(hh)
+    a, b = lib.lrb200_cmag_create(_lib.LRB200_DEVICE), lib.lrb200_cmag_create(_lib.LRB200_DEVICE)
+    assert lib.lrb200_graph_append(g, a) == 0
+    assert lib.lrb200_graph_append(g, b) != 0                             # float output cannot feed a complex input
+    lib.lrb200_block_destroy(b)
+    lib.lrb200_graph_destroy(g)
