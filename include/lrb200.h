@@ -144,8 +144,9 @@ lrb200_downsample_t* lrb200_downsample_create(unsigned factor, unsigned elem_siz
 /* ---- IIRFilterBlock / SinglepoleLowpass / SinglepoleHighpass / FMDeemphasisFilterBlock --------
  * Replaces iirfilt_{rrrf,crcf}_create/_execute_block (iirfilter.lua:63-109) and the Lua recurrence
  * (:113-179): y[n] = (sum_j b[j] x[n-j] - sum_{j>=1} a[j] y[n-j]) / a[0], zero initial state.
- * The recurrence is evaluated as a block-parallel affine scan with decoupled look-back (exact
- * recurrence, not a truncated warm-up).  nb <= 9, na <= 9. */
+ * Single pole (na <= 2): block-parallel affine scan (decoupled look-back, or a warm-up restart when the pole's
+ * memory is shorter than 512 samples).  Higher orders (na, nb <= 10): direct form I in time-parallel chunks
+ * with a warm-up measured from the filter's impulse response; short calls are the plain sequential recurrence. */
 typedef lrb200_block_t lrb200_iir_t;
 lrb200_iir_t* lrb200_iir_create_rrrf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags);
 lrb200_iir_t* lrb200_iir_create_crcf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags);

@@ -105,6 +105,22 @@ struct IirBlock : Block {
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
 };
 
+// IIRFilterBlock of any order (na > 2): direct form I, time-parallel chunks with a measured warm-up
+struct IirGeneralBlock : Block {
+    bool complex_data = false;
+    float b[10] = {0}, a[10] = {0};
+    int nb = 1, na = 1;
+    long long warm = -1;               // samples until the impulse response of 1/A(z) is below 1e-10 of its peak
+    void* d_xhist[2] = {nullptr, nullptr};
+    void* d_yhist[2] = {nullptr, nullptr};
+    int cur = 0;
+    IirGeneralBlock(bool cplx, const float* b, unsigned nb, const float* a, unsigned na, bool dev);
+    ~IirGeneralBlock() override;
+    int init() override;
+    int reset() override;
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
 struct C2fBlock : Block {
     int op = 0;                       // 0 = magnitude, 1 = real part
     C2fBlock(int op, bool dev);

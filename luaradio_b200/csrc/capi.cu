@@ -283,6 +283,67 @@ int IirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_
 }
 
 // ---------------------------------------------------------------------------------------------
+// IIR of any order
+// ---------------------------------------------------------------------------------------------
+IirGeneralBlock::IirGeneralBlock(bool cplx, const float* b_, unsigned nb_, const float* a_, unsigned na_, bool dev) {
+    name = cplx ? "iir_crcf(general)" : "iir_rrrf(general)";
+    in_size = out_size = cplx ? 8 : 4;
+    dev_ptrs = dev;
+    complex_data = cplx;
+    nb = (int)nb_;
+    na = (int)na_;
+    const double a0 = a_[0];
+    for (int j = 0; j < nb; ++j) b[j] = (float)((double)b_[j] / a0);
+    for (int j = 0; j < na; ++j) a[j] = (float)((double)a_[j] / a0);
+    // impulse response of 1/A(z) in float64: last index where |h| >= 1e-10 * peak
+    const int limit = 1 << 16;
+    std::vector<double> h(limit);
+    double peak = 0.0;
+    long long last = 0;
+    for (int i = 0; i < limit; ++i) {
+        double v = (i == 0) ? 1.0 : 0.0;
+        for (int j = 1; j < na && j <= i; ++j) v -= (double)a[j] * h[i - j];
+        h[i] = v;
+        if (std::fabs(v) > peak) peak = std::fabs(v);
+        if (!std::isfinite(v)) { last = limit; break; }
+        if (std::fabs(v) >= 1e-10 * peak) last = i;
+    }
+    warm = (last + na + nb >= limit - 1) ? -1 : last + na + nb;
+}
+int IirGeneralBlock::init() {
+    for (int i = 0; i < 2; ++i) {
+        LRB_CHECK(cudaMalloc(&d_xhist[i], 10 * in_size));
+        LRB_CHECK(cudaMemset(d_xhist[i], 0, 10 * in_size));
+        LRB_CHECK(cudaMalloc(&d_yhist[i], 10 * in_size));
+        LRB_CHECK(cudaMemset(d_yhist[i], 0, 10 * in_size));
+    }
+    return 0;
+}
+IirGeneralBlock::~IirGeneralBlock() {
+    for (int i = 0; i < 2; ++i) { cudaFree(d_xhist[i]); cudaFree(d_yhist[i]); }
+}
+int IirGeneralBlock::reset() {
+    consumed = 0;
+    cur = 0;
+    for (int i = 0; i < 2; ++i) {
+        LRB_CHECK(cudaMemsetAsync(d_xhist[i], 0, 10 * in_size, ctx().stream));
+        LRB_CHECK(cudaMemsetAsync(d_yhist[i], 0, 10 * in_size, ctx().stream));
+    }
+    return 0;
+}
+int IirGeneralBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
+    *n_out = n;
+    if (n == 0) return 0;
+    if (launch_iir_general(complex_data, dx, (long long)n, dy, b, nb, a, na, d_xhist[cur], d_yhist[cur], warm, s) != 0) return -1;
+    // carried state: last nb-1 inputs of [xhist | x], last na-1 outputs of [yhist | y] (oldest first)
+    if (nb > 1 && launch_hist_update(dx, (long long)n, d_xhist[cur], d_xhist[cur ^ 1], nb - 1, (int)in_size, s) != 0) return -1;
+    if (na > 1 && launch_hist_update(dy, (long long)n, d_yhist[cur], d_yhist[cur ^ 1], na - 1, (int)in_size, s) != 0) return -1;
+    cur ^= 1;
+    consumed += n;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // ComplexMagnitude / ComplexToReal
 // ---------------------------------------------------------------------------------------------
 C2fBlock::C2fBlock(int op_, bool dev) {
@@ -481,9 +542,10 @@ lrb200_downsample_t* lrb200_downsample_create(unsigned factor, unsigned elem_siz
 static lrb200_block_t* iir_create(bool cplx, const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags) {
     if (ensure_init() != 0) return nullptr;
     if (!b || nb == 0 || !a || na == 0) { set_error("iir: b and a taps must be non-empty"); return nullptr; }
-    if (nb > 9) { set_error("iir: at most 9 feed-forward taps"); return nullptr; }
-    if (na > 2) { set_error("iir: only single-pole (na <= 2) recurrences are implemented on the GPU in this build"); return nullptr; }
+    if (nb > 10 || na > 10) { set_error("iir: at most 10 feed-forward and 10 feedback taps"); return nullptr; }
     if (a[0].value == 0.0f) { set_error("iir: a[0] must be non-zero"); return nullptr; }
+    if (na > 2 || nb > 9)
+        return wrap(new (std::nothrow) IirGeneralBlock(cplx, (const float*)b, nb, (const float*)a, na, (flags & LRB200_DEVICE) != 0));
     return wrap(new (std::nothrow) IirBlock(cplx, (const float*)b, nb, (const float*)a, na, (flags & LRB200_DEVICE) != 0));
 }
 lrb200_iir_t* lrb200_iir_create_rrrf(const float32_t* b, unsigned nb, const float32_t* a, unsigned na, unsigned flags) { return iir_create(false, b, nb, a, na, flags); }

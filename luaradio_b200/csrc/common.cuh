@@ -77,6 +77,10 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
                 const void* xhist_in, void* xhist_out, const void* ystate_in, void* ystate_out,
                 long long first, int D, IirScanWork* w, cudaStream_t s);
 
+// general order (direct form I), time-parallel with a warm-up of `warm` samples (< 0: unknown -> sequential)
+int launch_iir_general(bool complex_data, const void* x, long long n, void* y, const float* b, int nb, const float* a, int na,
+                       const void* xhist, const void* yhist, long long warm, cudaStream_t s);
+
 // ---- synth.cu ---------------------------------------------------------------------------------
 int launch_synth_white(float2* dst, uint64_t n0, long long n, uint32_t seed, cudaStream_t s);
 int launch_synth_fm(float2* dst, uint64_t n0, long long n, uint32_t seed, double rate, double carrier,

@@ -298,7 +298,8 @@ struct FirFast {
 static constexpr int FFT_MAX_TAPS = 513;       // L >= 512: at most half of every block is overlap
 
 int FirBlock::fast_init() {
-    if (kind == FIR_CRCF && D > 1 && !rotate) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
+    // register-tiled direct kernel: decimators with <= 128 taps and plain FIRs with <= 32 taps (complex in, real taps)
+    if (kind == FIR_CRCF && !rotate) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
     if (M > FFT_MAX_TAPS) return 0;
     if (kind == FIR_HILBERT && D != 1) return 0;
     fast = new (std::nothrow) FirFast();
@@ -380,7 +381,7 @@ int FirBlock::set_algorithm(int a) {
 }
 
 int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long long n_out, cudaStream_t s) {
-    if (poly && D > 1 && algo != LRB200_FIR_FFT)
+    if (poly && algo != LRB200_FIR_FFT)
         return launch_polyphase_crcf(poly, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, (float2*)dy,
                                      first, n_out, false, 0, consumed, s);
     if (!fast || effective_algorithm() != LRB200_FIR_FFT) {

@@ -293,3 +293,94 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
 }
 
 }  // namespace lrb
+
+// =============================================================================================
+// General-order IIRFilterBlock (iirfilter.lua:113-179): direct form I,
+//     y[n] = (sum_{j<nb} b[j] x[n-j] - sum_{1<=j<na} a[j] y[n-j]) / a[0]
+// Time-parallel with a measured warm-up: the host simulates the impulse response of 1/A(z) in float64 and finds
+// the length W after which it stays below 1e-10 of its peak; the stream is cut into chunks, every thread runs the
+// sequential recurrence over its chunk starting W samples early from (true past inputs, zero past outputs), and
+// only stores its own chunk.  Chunk 0 starts from the carried state, so short calls (the reference's 256-sample
+// vectors, or sample-by-sample streaming) are the plain sequential recurrence, bit for bit.  A filter whose
+// response never decays gets W = infinity -> one chunk.  Not on the WBFM chain (single-pole de-emphasis uses the
+// scan kernel above); this is the catch-all that makes every IIRFilterBlock signature run on the GPU.
+// =============================================================================================
+namespace lrb {
+
+namespace {
+
+constexpr int IIRG_MAX = 10;
+
+struct IirGenParams {
+    float b[IIRG_MAX];     // b[j] / a0
+    float a[IIRG_MAX];     // a[j] / a0 (a[0] unused)
+    int nb, na;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+iir_general_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirGenParams P,
+                   const T* __restrict__ xhist, const T* __restrict__ yhist, long long chunk, long long warm) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long start = g * chunk;
+    if (start >= n) return;
+    const long long end = (start + chunk < n) ? start + chunk : n;
+    long long begin = start - warm;
+    const bool from_state = begin <= 0;
+    if (from_state) begin = 0;
+    T xs[IIRG_MAX], ys[IIRG_MAX];
+#pragma unroll
+    for (int j = 0; j < IIRG_MAX; ++j) { xs[j] = zero_of(T()); ys[j] = zero_of(T()); }
+    const int nh = P.nb - 1, ny = P.na - 1;
+    // xs[j] = x[i-1-j], ys[j] = y[i-1-j] at i = begin
+#pragma unroll
+    for (int j = 0; j < IIRG_MAX - 1; ++j) {
+        if (j < nh) {
+            const long long i = begin - 1 - j;
+            xs[j] = (i >= 0) ? __ldg(x + i) : ((nh + i >= 0) ? __ldg(xhist + (nh + i)) : zero_of(T()));
+        }
+        if (j < ny && from_state) ys[j] = __ldg(yhist + (ny - 1 - j));
+    }
+    for (long long i = begin; i < end; ++i) {
+        const T xi = __ldg(x + i);
+        T acc = fmas(P.b[0], xi, zero_of(T()));
+#pragma unroll
+        for (int j = 1; j < IIRG_MAX; ++j) if (j < P.nb) acc = fmas(P.b[j], xs[j - 1], acc);
+#pragma unroll
+        for (int j = 1; j < IIRG_MAX; ++j) if (j < P.na) acc = fmas(-P.a[j], ys[j - 1], acc);
+#pragma unroll
+        for (int j = IIRG_MAX - 1; j > 0; --j) { xs[j] = xs[j - 1]; ys[j] = ys[j - 1]; }
+        xs[0] = xi;
+        ys[0] = acc;
+        if (i >= start) y[i] = acc;
+    }
+}
+
+}  // namespace
+
+int launch_iir_general(bool complex_data, const void* x, long long n, void* y, const float* b, int nb, const float* a, int na,
+                       const void* xhist, const void* yhist, long long warm, cudaStream_t s) {
+    if (n <= 0) return 0;
+    IirGenParams P;
+    for (int j = 0; j < IIRG_MAX; ++j) { P.b[j] = j < nb ? b[j] : 0.f; P.a[j] = j < na ? a[j] : 0.f; }
+    P.nb = nb;
+    P.na = na;
+    long long chunk = n, w = warm;
+    if (warm >= 0 && warm < n) {
+        chunk = 4 * warm > 512 ? 4 * warm : 512;
+    } else {
+        w = n;                                       // no decay information: one sequential chunk
+    }
+    const long long nchunks = (n + chunk - 1) / chunk;
+    const int threads = 128;
+    const long long blocks = (nchunks + threads - 1) / threads;
+    if (complex_data)
+        iir_general_kernel<float2><<<(unsigned)blocks, threads, 0, s>>>((const float2*)x, n, (float2*)y, P, (const float2*)xhist, (const float2*)yhist, chunk, w);
+    else
+        iir_general_kernel<float><<<(unsigned)blocks, threads, 0, s>>>((const float*)x, n, (float*)y, P, (const float*)xhist, (const float*)yhist, chunk, w);
+    count_launch();
+    LRB_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace lrb

@@ -322,7 +322,8 @@ struct PolyTaps {
 };
 
 static int shape_q(int M, int D) {
-    // instantiated (D, Q) shapes: Q = ceil(Mpad / D) for Mpad in {64, 128}
+    // instantiated (D, Q) shapes: Q = ceil(Mpad / D) for Mpad in {64, 128}; D = 1 (plain short FIR): Q in {16, 32}
+    if (D == 1) return M <= 16 ? 16 : (M <= 32 ? 32 : 0);
     if (D != 2 && D != 3 && D != 4 && D != 5 && D != 8 && D != 10) return 0;
     if (M <= 64) return (64 + D - 1) / D;
     if (M <= 128) return (128 + D - 1) / D;
@@ -371,6 +372,7 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
     if (n_out <= 0) return 1;
     PolyParams P = p->P;
     P.g0 = g0;
+    LRB_SHAPE(1, 16) LRB_SHAPE(1, 32)
     LRB_SHAPE(2, 32) LRB_SHAPE(2, 64)
     LRB_SHAPE(3, 22) LRB_SHAPE(3, 43)
     LRB_SHAPE(4, 16) LRB_SHAPE(4, 32)

@@ -15,7 +15,7 @@ BLOCK_SPECS = [
     "firfilter_spec", "lowpassfilter_spec", "highpassfilter_spec", "bandpassfilter_spec", "bandstopfilter_spec",
     "complexbandpassfilter_spec", "complexbandstopfilter_spec", "hilberttransform_spec", "frequencytranslator_spec",
     "frequencydiscriminator_spec", "downsampler_spec", "fmdeemphasisfilter_spec", "singlepolelowpassfilter_spec",
-    "singlepolehighpassfilter_spec", "complexmagnitude_spec", "complextoreal_spec",
+    "singlepolehighpassfilter_spec", "iirfilter_spec", "complexmagnitude_spec", "complextoreal_spec",
 ]
 
 

@@ -285,3 +285,22 @@ def test_c_abi_argument_errors():
     assert lib.lrb200_graph_append(g, b) != 0                             # float output cannot feed a complex input
     lib.lrb200_block_destroy(b)
     lib.lrb200_graph_destroy(g)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_general_iir_long_stream(cplx):
+    """IIRFilterBlock of order 2/4/8 on a long stream: the time-parallel chunks (warm-up restart) must agree with
+    the sequential recurrence, for one big call and for ragged streaming."""
+    import scipy.signal
+    rng = np.random.default_rng(12)
+    n = 300000
+    x = rnd_c(rng, n) if cplx else rng.uniform(-1, 1, n).astype(np.float32)
+    t = ComplexFloat32 if cplx else Float32
+    for order, wn in ((2, 0.3), (4, 0.2), (8, 0.45)):
+        b, a = scipy.signal.butter(order, wn)
+        b, a = b.astype(np.float32), a.astype(np.float32)
+        ref = O.IIRFilterFast(b, a, cplx).process(x)
+        for cuts in ([(0, n)], ragged(rng, n, 0, 70000)):
+            blk = mk(radio.IIRFilterBlock, [Float32.vector_from_array(b), Float32.vector_from_array(a)], t)
+            close(stream(blk, x, cuts), ref)
+            blk.cleanup()
