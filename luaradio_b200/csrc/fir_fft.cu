@@ -24,6 +24,7 @@
 #include "fft32_gen.cuh"
 #include "../../include/lrb200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <new>
@@ -59,6 +60,9 @@ struct FftArgs {
     long long first;          // decimation: keep outputs at input index first + j*D
     uint64_t turns_fix, g0;   // fused translator
     int M, D;
+    int hist_len;             // samples in `hist` (total taps - 1; > M-1 for one partition of a long filter)
+    int in_shift;             // partitioned long filters: this launch convolves taps [in_shift, in_shift + M) 
+    int accumulate;           // ... and adds into y instead of overwriting it
 };
 
 // floor division helpers for (possibly negative) t and positive d
@@ -75,7 +79,7 @@ __device__ __forceinline__ void floor_divmod(long long t, int d, long long* q, i
 // EDGE false: interior blocks [b_lo, b_hi): all N inputs inside x, unconditional coalesced loads (one code path:
 //             guarded loads made the compiler clone the butterfly networks behind each branch);
 //      true : blocks touching the carried history (b = 0) or the end of the input (b >= b_hi), bounds-checked;
-//             work index e = 0 -> block 0, e >= 1 -> block b_hi + e - 1.
+//             work index e < b_lo -> block e, else block b_hi + (e - b_lo).
 // ROT  (IN 0): fused FrequencyTranslator: x[i] * exp(j w (g0+i)) = P_b * (x[i] * E[i - base]); E is applied at the
 //             load, the per-block phasor P_b commutes with the (linear) filter and is applied to kept outputs only.
 // DEC  fused Downsampler: only outputs at input index first + j*D are stored, at y[j].
@@ -103,22 +107,24 @@ fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
     const int s32 = DEC ? 32 % D : 0, q32 = DEC ? 32 / D : 0;
     const long long wstride = (long long)gridDim.x * FF_WARPS;
     for (long long wi = (long long)blockIdx.x * FF_WARPS + warp; wi < A.nwork; wi += wstride) {
-        const long long b = EDGE ? (wi == 0 ? 0 : A.b_hi + wi - 1) : (A.b_lo + wi);
+        const long long b = EDGE ? (wi < A.b_lo ? wi : A.b_hi + (wi - A.b_lo)) : (A.b_lo + wi);
         float2 v[32];
         // ---- load: v[r] = X[base + 32 r + lane]
         if constexpr (IN == 0) {
             const float2* x = reinterpret_cast<const float2*>(A.x);
             const float2* hist = reinterpret_cast<const float2*>(A.hist);
-            const long long base = b * L - Hm1;
+            const long long base = b * L - Hm1 - A.in_shift;
             if constexpr (!EDGE) {
                 const float2* xb = x + base + lane;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) v[r] = __ldcs(xb + 32 * r);
             } else {
+                const int HL = A.hist_len;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     const long long i = base + 32 * r + lane;
-                    v[r] = (i >= 0) ? (i < n ? __ldg(x + i) : make_float2(0.f, 0.f)) : __ldg(hist + (Hm1 + i));
+                    v[r] = (i >= 0) ? (i < n ? __ldg(x + i) : make_float2(0.f, 0.f))
+                                    : ((HL + i >= 0) ? __ldg(hist + (HL + i)) : make_float2(0.f, 0.f));
                 }
             }
             if constexpr (ROT) {
@@ -137,7 +143,7 @@ fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
                     v[r] = make_float2(__ldcs(x + i0), __ldcs(x + i1));
                 } else {
                     const float a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : 0.f) : __ldg(hist + (Hm1 + i0));
-                    const float c = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : 0.f) : __ldg(hist + (Hm1 + i1));
+                    const float c = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : 0.f) : ((Hm1 + i1 >= 0) ? __ldg(hist + (Hm1 + i1)) : 0.f);
                     v[r] = make_float2(a, c);
                 }
             }
@@ -196,7 +202,11 @@ fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
                 for (int n1 = 0; n1 < 32; ++n1) {
                     const int nn = 32 * n1 + lane;
                     const long long o = obase + nn;
-                    if (nn >= Hm1 && (!EDGE || o < n)) __stcs(y + o, v[bitrev5(n1)]);
+                    if (nn >= Hm1 && (!EDGE || o < n)) {
+                        float2 t = v[bitrev5(n1)];
+                        if (A.accumulate) t = __fadd2_rn(t, y[o]);
+                        __stcs(y + o, t);
+                    }
                 }
             } else {
                 float2 Pb = make_float2(1.f, 0.f);
@@ -289,7 +299,9 @@ int launch_fft(const FftArgs& base_args, long long n_int, long long n_edge, cuda
 // firfilter.lua:337-343 does with spectrum_utils.DFT) and the 32x32 inter-pass twiddle table.
 // ---------------------------------------------------------------------------------------------
 struct FirFast {
-    float2* d_H = nullptr;
+    int nparts = 1;            // > 1: uniformly partitioned overlap-save for filters longer than one block allows
+    int part_taps = 0;
+    float2* d_H = nullptr;     // nparts tap spectra, FF_N each
     float2* d_tw = nullptr;
     float2* d_E = nullptr;
     int in_mode = 0;
@@ -300,11 +312,15 @@ static constexpr int FFT_MAX_TAPS = 513;       // L >= 512: at most half of ever
 int FirBlock::fast_init() {
     // register-tiled direct kernel: decimators with <= 128 taps and plain FIRs with <= 32 taps (complex in, real taps)
     if (kind == FIR_CRCF && !rotate) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
-    if (M > FFT_MAX_TAPS) return 0;
     if (kind == FIR_HILBERT && D != 1) return 0;
+    const bool long_filter = M > FFT_MAX_TAPS;
+    // long filters: complex-input, no fused decimation/translator -> P partitions of 512 taps, P passes over x
+    if (long_filter && !((kind == FIR_CRCF || kind == FIR_CCCF) && D == 1 && !rotate && M <= 16 * 512)) return 0;
     fast = new (std::nothrow) FirFast();
     if (!fast) { set_error("out of memory"); return -1; }
     fast->in_mode = (kind == FIR_RRRF) ? 1 : (kind == FIR_HILBERT ? 2 : 0);
+    fast->part_taps = long_filter ? 512 : M;
+    fast->nparts = long_filter ? (M + 511) / 512 : 1;
     const double two_pi = 6.283185307179586476925286766559;
     std::vector<std::complex<double>> h(M);
     const float* tf = (const float*)h_taps.data();
@@ -313,25 +329,28 @@ int FirBlock::fast_init() {
         else if (kind == FIR_HILBERT) h[k] = std::complex<double>(k == (M - 1) / 2 ? 1.0 : 0.0, tf[k]);   // delay + j*hilbert (hilberttransform.lua:120-124)
         else h[k] = std::complex<double>(tf[k], 0.0);
     }
-    std::vector<float2> H(FF_N), tw(FF_N), E(FF_N);
-    for (int k = 0; k < FF_N; ++k) {
-        std::complex<double> acc(0.0, 0.0);
-        for (int m = 0; m < M; ++m) {
-            const int e = (int)(((long long)k * m) % FF_N);
-            acc += h[m] * std::complex<double>(std::cos(two_pi * e / FF_N), -std::sin(two_pi * e / FF_N));
+    std::vector<float2> H((size_t)FF_N * fast->nparts), tw(FF_N), E(FF_N);
+    std::vector<std::complex<double>> wtab(FF_N);
+    for (int e = 0; e < FF_N; ++e) wtab[e] = std::complex<double>(std::cos(two_pi * e / FF_N), -std::sin(two_pi * e / FF_N));
+    for (int part = 0; part < fast->nparts; ++part) {
+        const int m0 = part * fast->part_taps;
+        const int mc = std::min(fast->part_taps, M - m0);
+        for (int k = 0; k < FF_N; ++k) {
+            std::complex<double> acc(0.0, 0.0);
+            for (int m = 0; m < mc; ++m) acc += h[m0 + m] * wtab[(int)(((long long)k * m) % FF_N)];
+            acc /= (double)FF_N;
+            const int k1 = k % 32, k2 = k / 32;
+            H[(size_t)part * FF_N + k2 * 32 + k1] = make_float2((float)acc.real(), (float)acc.imag());
         }
-        acc /= (double)FF_N;
-        const int k1 = k % 32, k2 = k / 32;
-        H[k2 * 32 + k1] = make_float2((float)acc.real(), (float)acc.imag());
     }
     for (int a = 0; a < 32; ++a)
         for (int c = 0; c < 32; ++c) {
             const int e = (a * c) % FF_N;
             tw[a * 32 + c] = make_float2((float)std::cos(two_pi * e / FF_N), (float)(-std::sin(two_pi * e / FF_N)));
         }
-    LRB_CHECK(cudaMalloc(&fast->d_H, sizeof(float2) * FF_N));
+    LRB_CHECK(cudaMalloc(&fast->d_H, sizeof(float2) * H.size()));
     LRB_CHECK(cudaMalloc(&fast->d_tw, sizeof(float2) * FF_N));
-    LRB_CHECK(cudaMemcpy(fast->d_H, H.data(), sizeof(float2) * FF_N, cudaMemcpyHostToDevice));
+    LRB_CHECK(cudaMemcpy(fast->d_H, H.data(), sizeof(float2) * H.size(), cudaMemcpyHostToDevice));
     LRB_CHECK(cudaMemcpy(fast->d_tw, tw.data(), sizeof(float2) * FF_N, cudaMemcpyHostToDevice));
     if (rotate) {
         // E[n] = exp(j 2 pi turns n) from the same 2^-64 fixed-point turns the kernel uses for the block phasor
@@ -370,7 +389,8 @@ int FirBlock::effective_algorithm() const {
     // The only direct kernel for these shapes is the catch-all (about 8x off its FP32 bound), hence the factor.
     const double per_tap = kind == FIR_CCCF ? 2.0 : (kind == FIR_CRCF ? 1.0 : 0.5);
     const double direct_cost = 8.0 * per_tap * M / D;
-    const double fft_cost = 31.0 * FF_N / (double)(FF_N - M + 1) * (kind == FIR_RRRF ? 0.5 : 1.0);
+    const int mp = fast->part_taps;
+    const double fft_cost = fast->nparts * 31.0 * FF_N / (double)(FF_N - mp + 1) * (kind == FIR_RRRF ? 0.5 : 1.0);
     return direct_cost > fft_cost ? LRB200_FIR_FFT : LRB200_FIR_DIRECT;
 }
 
@@ -388,30 +408,45 @@ int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long
         if (rotate) { set_error("fir: fused translator needs the overlap-save path (ntaps <= %d)", FFT_MAX_TAPS); return -1; }
         return 0;
     }
-    const int L = FF_N - (M - 1);
+    const int Mp = fast->part_taps;                      // taps convolved per launch (== M unless partitioned)
+    const int L = FF_N - (Mp - 1);
     // a forced FFT (or a fused translator) always runs; the automatic choice leaves short calls to the direct kernel
     if (algo != LRB200_FIR_FFT && !rotate && (long long)n < 8LL * L) return 0;
     // blocks of L outputs; in packed-real mode one FFT covers two of them
     const long long per = (fast->in_mode == 1) ? 2LL * L : (long long)L;
     const long long nblocks = ((long long)n + per - 1) / per;
-    long long b_hi = (long long)n / per;                 // blocks [1, b_hi) are interior
-    if (b_hi < 1) b_hi = 1;
-    if (b_hi > nblocks) b_hi = nblocks;
-    FftArgs a;
-    a.x = dx; a.hist = d_hist[cur]; a.y = dy; a.H = fast->d_H; a.tw = fast->d_tw; a.E = fast->d_E;
-    a.n = (long long)n; a.b_lo = 1; a.b_hi = b_hi; a.nwork = 0; a.first = first;
-    a.turns_fix = rot_fix; a.g0 = consumed; a.M = M; a.D = D;
-    const long long n_int = b_hi - 1, n_edge = 1 + (nblocks - b_hi);
-    const bool dec = D > 1;
-    switch (fast->in_mode) {
-        case 0:
-            if (rotate) return launch_fft<0, true, true>(a, n_int, n_edge, s);       // fused translator always uses the DEC store (D may be 1)
-            return dec ? launch_fft<0, false, true>(a, n_int, n_edge, s) : launch_fft<0, false, false>(a, n_int, n_edge, s);
-        case 1:
-            return dec ? launch_fft<1, false, true>(a, n_int, n_edge, s) : launch_fft<1, false, false>(a, n_int, n_edge, s);
-        default:
-            return launch_fft<2, false, false>(a, n_int, n_edge, s);
+    for (int part = 0; part < fast->nparts; ++part) {
+        const int shift = part * Mp;
+        // interior blocks [b_lo, b_hi): b*per - (Mp-1) - shift >= 0  and  (b+1)*per <= n
+        long long b_lo = ((long long)(Mp - 1) + shift + per - 1) / per;
+        if (b_lo < 1) b_lo = 1;
+        long long b_hi = (long long)n / per;
+        if (b_hi > nblocks) b_hi = nblocks;
+        if (b_hi < b_lo) b_hi = b_lo;
+        if (b_lo > nblocks) { b_lo = nblocks; b_hi = nblocks; }
+        FftArgs a;
+        a.x = dx; a.hist = d_hist[cur]; a.y = dy; a.H = fast->d_H + (size_t)part * FF_N; a.tw = fast->d_tw; a.E = fast->d_E;
+        a.n = (long long)n; a.b_lo = b_lo; a.b_hi = b_hi; a.nwork = 0; a.first = first;
+        a.turns_fix = rot_fix; a.g0 = consumed; a.M = Mp; a.D = D;
+        a.hist_len = M - 1; a.in_shift = shift; a.accumulate = part > 0 ? 1 : 0;
+        // edge work list: blocks [0, b_lo) and [b_hi, nblocks); the kernel maps e -> (e < b_lo ? e : b_hi + e - b_lo)
+        const long long n_int = b_hi - b_lo, n_edge = b_lo + (nblocks - b_hi);
+        const bool dec = D > 1;
+        int rc;
+        switch (fast->in_mode) {
+            case 0:
+                if (rotate) rc = launch_fft<0, true, true>(a, n_int, n_edge, s);   // fused translator always uses the DEC store (D may be 1)
+                else rc = dec ? launch_fft<0, false, true>(a, n_int, n_edge, s) : launch_fft<0, false, false>(a, n_int, n_edge, s);
+                break;
+            case 1:
+                rc = dec ? launch_fft<1, false, true>(a, n_int, n_edge, s) : launch_fft<1, false, false>(a, n_int, n_edge, s);
+                break;
+            default:
+                rc = launch_fft<2, false, false>(a, n_int, n_edge, s);
+        }
+        if (rc < 0) return -1;
     }
+    return 1;
 }
 
 }  // namespace lrb
