@@ -135,7 +135,7 @@ struct lrb200_block_s { lrb::Block* impl; };
 namespace lrb {
 // tuner.cu: register-tiled polyphase decimating FIR (complex in, real taps), optional fused rotator.
 // Returns 1 if the (M, D) shape is supported and the launch was enqueued, 0 if unsupported, <0 on error.
-PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample);
+PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table = false);
 void polyphase_release(PolyTaps* p);
 int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist, long long n, float2* y,
                           long long first, long long n_out, bool rotate, uint64_t turns_fix, uint64_t g0,

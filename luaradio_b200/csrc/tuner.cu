@@ -1,28 +1,44 @@
 // Register-tiled polyphase decimating FIR (complex in, real taps) with an optional fused frequency
-// translator: the TunerBlock / DecimatorBlock kernel.
+// translator in front and an optional fused frequency discriminator behind: the TunerBlock / DecimatorBlock
+// kernel, and the dominant kernel of the WBFM-mono chain.
 //
-// Reference dataflow being fused (composites/tuner.lua:40-47):
-//     FrequencyTranslatorBlock(offset) -> LowpassFilterBlock(128, bw/2) -> DownsamplerBlock(D)
-// i.e. three processes and two socket hops, with the FIR computing D times more outputs than are
-// kept (firfilter.lua:121-124 runs one dot product per INPUT sample).  Here only the kept outputs are
-// computed (M/D complex-by-real MACs per input sample), the rotation is applied once per input sample
-// while the tile is staged into shared memory, and the input is read from HBM exactly once:
-// algorithmic traffic 8 + 8/D bytes per input sample.
+// Reference dataflow being fused (composites/tuner.lua:40-47, examples/rtlsdr_wbfm_mono.lua:12-14):
+//     FrequencyTranslatorBlock(offset) -> LowpassFilterBlock(128, bw/2) -> DownsamplerBlock(D) [-> FrequencyDiscriminator]
+// i.e. three (four) processes and socket hops, with the FIR computing D times more outputs than are kept
+// (firfilter.lua:121-124 runs one dot product per INPUT sample).  Here only the kept outputs are computed
+// (M/D complex-by-real MACs per input sample) and the input is read from HBM exactly once:
+// algorithmic traffic 8 + 8/D bytes per input sample (8 + 4/D with the discriminator fused).
 //
-// Tiling.  A CTA produces TO = 128 threads x R = 8 consecutive decimated outputs.  With reversed,
-// zero-padded taps hr[0 .. Q*D), Q = ceil(M/D), and B the first input index the tile needs,
-//     y[m0 + r] = sum_p sum_q hr[q*D + p] * S_p[r + q],      S_p[j] = X[B + j*D + p]
-// so the tile is staged de-interleaved by polyphase branch p.  Per branch a thread slides an R-wide
-// register window over S_p: one new 8-byte LDS per R FFMA2 (the complex sample is one packed f32x2
-// register, the real tap is the scalar-broadcast operand of FFMA2).  Branch arrays are padded by
-// 2 samples every 8 so that the per-thread stride is 10 samples = 20 banks and 128-bit shared loads of
-// a quarter warp fall in distinct banks.  Taps live in the kernel-parameter constant bank.
+// Tile.  A CTA produces PT_TO = 128 threads x R = 8 consecutive decimated outputs from one shared-memory tile of
+// rotated input samples kept in their natural (interleaved) order.  With reversed taps hr[0 .. T), T = Q*D + 1
+// (Q = ceil(M/D); one spare leading tap lets the host make every tile start on an even input index, so every
+// global load is an aligned 128-bit load and there is a single code path), and B the first input the tile needs,
+//     y[m0 + r] = sum_{i' < T} hr[i'] * X[B + r*D + i'].
+// A thread walks window positions j = 0 .. R+Q-1; at each it loads the D consecutive samples X[B + (tR + j)D + p]
+// (40 contiguous bytes for D = 5: two LDS.128 + one LDS.64) and feeds them to every output r with 0 <= j-r <= Q:
+// one packed FFMA2 (f32x2 complex sample x scalar-broadcast real tap from the constant bank) per MAC, no
+// register window to rotate, no de-interleaving.  Thread t's samples start at element t*(R*D) and the layout is
+// padded by 2 samples every R*D, which makes the per-thread stride (R*D+2)*8 B conflict-free for 128-bit loads.
+//
+// Rotation.  x[i] e^{jw(g0+i)} = P_tile * (x[i] * E[i - B]) with E a per-handle table of the tile-relative phasors
+// (L2 resident) and P_tile the phasor of the tile origin; E is applied while staging (one complex multiply per
+// sample), P_tile commutes with the filter and is applied to the 1/D kept outputs.
+//
+// History of this kernel (ncu summaries in profiles/): v1 guarded loads, 1.43 ms per 256 Mi samples, 85 % of
+// stall samples on first use of a load; v2 batched loads 0.90 ms; v3 persistent + cross-tile prefetch + fused
+// discriminator 1.00 ms (0.90 + 0.13 before); a warp-specialised producer/consumer variant of v3 gained only 5 %
+// because v3 was issue-bound, not latency-bound: 60 instructions per staged sample PAIR (de-interleave index
+// arithmetic + two phasor products).  v4 (this file) stages with ~13.
 #include "common.cuh"
 #include "blocks.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
+#include <type_traits>
+#include <vector>
 
 namespace lrb {
 
@@ -30,82 +46,70 @@ namespace {
 
 constexpr int PT_THREADS = 128;
 constexpr int PT_R = 8;
-constexpr int PT_TO = PT_THREADS * PT_R;     // outputs per tile
-constexpr int PT_MAXTAPS = 144;              // Q*D upper bound for the instantiated shapes
-constexpr int PT_MAXIT = 48;                 // staging iterations (pairs per thread) upper bound
+constexpr int PT_TO = PT_THREADS * PT_R;     // filter outputs per tile
+constexpr int PT_MAXTAPS = 144;              // Q*D + 1 upper bound for the instantiated shapes
+constexpr int PT_BATCH = 7;                  // 128-bit loads issued back to back per staging batch
 
 struct PolyParams {
-    float hr[PT_MAXTAPS];        // reversed taps, zero padded to Q*D
-    float2 step[PT_MAXIT];       // exp(j*2*pi*turns * 2*PT_THREADS*it): staging-iteration phasor
-    float2 rot1;                 // exp(j*2*pi*turns): one-sample rotation
+    float hr[PT_MAXTAPS];        // reversed taps with the launch's alignment shift, zero padded to Q*D + 1
     uint64_t turns_fix;          // turns per sample, 2^-64 units
     uint64_t g0;                 // global index of x[0]
+    long long off;               // B(tile) = off + tile * TS * D   (even)
     int M;
 };
 
-__host__ __device__ constexpr int pad_idx(int j) { return j + 2 * (j / 8); }
-
 template <int D, int Q>
 struct PolyShape {
-    static constexpr int J = PT_TO + Q;                    // samples per branch (one spare)
-    static constexpr int JP = (pad_idx(J) + 3) & ~1;       // padded branch length (even: keeps 16 B alignment)
-    static constexpr int SPAN = (PT_TO + Q - 1) * D + 2;   // input samples staged per tile (incl. alignment slack)
+    static constexpr int RD = PT_R * D;                          // samples per thread per window step block
+    static constexpr int T = Q * D + 1;                          // taps incl. the alignment spare
+    static constexpr int SPAN = (PT_TO + Q - 1) * D + 1;         // samples a tile needs: e in [0, SPAN)
     static constexpr int PAIRS = (SPAN + 1) / 2;
     static constexpr int ITERS = (PAIRS + PT_THREADS - 1) / PT_THREADS;
-    static constexpr size_t SMEM = (size_t)D * JP * sizeof(float2);
+    static constexpr int LOADED = 2 * ITERS * PT_THREADS;        // samples actually staged (>= SPAN)
+    __host__ __device__ static constexpr int pad(int e) { return e + 2 * (e / RD); }
+    static constexpr int ELEMS = LOADED + 2 * (LOADED / RD) + 2;
+    static constexpr size_t SMEM = (size_t)ELEMS * sizeof(float2);
 };
 
-// One tile = PT_TO complex filter outputs starting at output index m0.  With the fused discriminator
-// (DISC) consecutive tiles overlap by ONE output (tile stride PT_TO - 1): slot 0 of a tile is the output just
-// before its first discriminator output, so y[m-1] is always in a neighbouring register (or one shuffle /
-// one shared-memory word away) and never has to be fetched from another CTA.
-//
-// Interior kernel (EDGE = false): persistent CTAs, grid-stride over the interior tiles.  Staging is batches
-// of unconditional 128-bit streaming loads; the first two batches of the NEXT tile are issued before the
-// compute phase of the current one and stay in registers across it, so HBM latency overlaps the FFMA2 loop
-// (ncu on the first version: 85 % of stall samples on the first use of a guarded load; on the second, still
-// ~32 % -- hence the cross-tile prefetch).  Edge kernel (EDGE = true): the few tiles that touch the carried
-// history or the end of the input; every load bounds-checked, one tile per CTA.
-constexpr int PT_BATCH = 7;
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E) -- guarantees full unrolling with
+// constant register indices (a plain `#pragma unroll` gave up on the 34 x 8 x 5 nest and spilled to indexing)
+template <int B, int E, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
 
-template <int D, int Q, bool ROT, bool DISC>
-struct TileCtx {
-    long long m0, B, Beven;
-    int shift;
-};
+// DISC: consecutive tiles overlap by two outputs (tile stride PT_TO - 2, even so that tile origins keep their
+// parity): slot 0 is the output just before the tile's first discriminator output, slot PT_TO-1 is unused.
+template <bool DISC>
+struct TileStride { static constexpr int TS = DISC ? PT_TO - 2 : PT_TO; };
 
 template <int D, int Q, bool ROT, bool DISC, bool EDGE>
 __global__ void __launch_bounds__(PT_THREADS, 4)
 polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, long long n,
-                      void* __restrict__ yv, long long first, long long n_out,
-                      const __grid_constant__ PolyParams P, long long t_lo, long long t_hi,
+                      void* __restrict__ yv, long long n_out, const __grid_constant__ PolyParams P,
+                      const float2* __restrict__ E, long long t_lo, long long t_hi,
                       const float2* __restrict__ prev_in, float2* __restrict__ prev_out, float inv_gain) {
     using S = PolyShape<D, Q>;
-    constexpr int TS = DISC ? PT_TO - 1 : PT_TO;       // tile stride in outputs
+    constexpr int TS = TileStride<DISC>::TS;
     constexpr int NPRE = S::ITERS < PT_BATCH ? S::ITERS : PT_BATCH;
     extern __shared__ __align__(16) float2 smem[];
     __shared__ float2 s_edge[PT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int M = P.M;
-    const int Hm1 = M - 1;
-    constexpr int ADV_J = (2 * PT_THREADS) / D, ADV_P = (2 * PT_THREADS) % D;
+    const int Hm1 = P.M - 1;
 
-    auto tile_of = [&](long long idx) -> long long {
-        return EDGE ? (idx < t_lo ? idx : t_hi + (idx - t_lo)) : (t_lo + idx);
-    };
+    auto tile_of = [&](long long idx) -> long long { return EDGE ? (idx < t_lo ? idx : t_hi + (idx - t_lo)) : (t_lo + idx); };
     const long long n_work = EDGE ? 0 : (t_hi - t_lo);
     long long widx = blockIdx.x;
+
+    // staging addresses: pair u = tid + 128*it holds samples e = 2u, 2u+1 -> padded element 2u + 2*floor(2u / RD)
+    // (RD is even, so a pair never straddles a padding gap and stays 16-byte aligned)
     float4 pre[NPRE];
-    auto first_input = [&](long long tile) -> long long {
-        // first input index needed by slot 0 of the tile, taps padded to Q*D at the OLD end:
-        // y[m] = sum_{i'} hr[i'] X[c_m - (Q*D - 1) + i'],  c_m = first + m*D,  m = tile*TS - (DISC ? 1 : 0)
-        const long long m0 = tile * TS - (DISC ? 1 : 0);
-        return first + m0 * (long long)D - (long long)(Q * D - 1);
-    };
     if constexpr (!EDGE) {
         if (widx < n_work) {
-            const long long Bev = first_input(tile_of(widx)) & ~1LL;
-            const float4* x4 = reinterpret_cast<const float4*>(x + Bev) + tid;
+            const float4* x4 = reinterpret_cast<const float4*>(x + (P.off + tile_of(widx) * (long long)(TS * D))) + tid;
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) pre[k] = __ldcs(x4 + k * PT_THREADS);
         }
@@ -114,45 +118,24 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
     for (;;) {
         if constexpr (!EDGE) { if (widx >= n_work) break; }
         const long long tile = tile_of(widx);
-        const long long m0 = tile * TS - (DISC ? 1 : 0);          // output index of slot 0
-        const long long B = first_input(tile);
-        const long long Beven = B & ~1LL;              // floor to even (two's complement: correct for negatives)
-        const int shift = (int)(B - Beven);            // 0 or 1
+        const long long B = P.off + tile * (long long)(TS * D);      // first input index of the tile (even)
+        const long long m0 = tile * TS - (DISC ? 1 : 0);             // output index of slot 0
 
-        // ---- stage: global -> (rotate) -> de-interleaved shared memory
-        float2 c0 = make_float2(1.f, 0.f), c1 = make_float2(1.f, 0.f);
-        if constexpr (ROT) {
-            // phasor of this thread's first sample pair; later pairs advance by the per-iteration step table
-            uint64_t g = P.g0 + (uint64_t)(Beven + 2LL * tid);
-            c0 = phasor_from_fix(P.turns_fix * g);
-            c1 = cmul(c0, P.rot1);
-        }
-        // tile-relative index of the pair's first sample, e0 = 2u - shift, tracked as (j, p) = (e0 / D, e0 % D)
-        int ej, ep;
-        {
-            const int e0 = 2 * tid - shift + D;        // + D keeps the division non-negative (e0 >= -1)
-            ej = e0 / D - 1;
-            ep = e0 - (ej + 1) * D;
-        }
+        // ---- stage: global -> (x E) -> shared, natural order
         auto stage_pair = [&](float4 v, int it) {
+            const int u = tid + it * PT_THREADS;
             float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
             if constexpr (ROT) {
-                const float2 st = P.step[it];
-                a = cmul(a, cmul(c0, st));
-                b = cmul(b, cmul(c1, st));
+                const float4 e = __ldg(reinterpret_cast<const float4*>(E) + u);
+                a = cmul(a, make_float2(e.x, e.y));
+                b = cmul(b, make_float2(e.z, e.w));
             }
-            if (ej >= 0 && ej < S::J) smem[ep * S::JP + pad_idx(ej)] = a;
-            int j1 = ej, p1 = ep + 1;
-            if (p1 == D) { p1 = 0; ++j1; }
-            if (j1 >= 0 && j1 < S::J) smem[p1 * S::JP + pad_idx(j1)] = b;
-            ej += ADV_J;
-            ep += ADV_P;
-            if (ep >= D) { ep -= D; ++ej; }
+            *reinterpret_cast<float4*>(smem + S::pad(2 * u)) = make_float4(a.x, a.y, b.x, b.y);
         };
         if constexpr (!EDGE) {
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], k);
-            const float4* x4 = reinterpret_cast<const float4*>(x + Beven) + tid;
+            const float4* x4 = reinterpret_cast<const float4*>(x + B) + tid;
 #pragma unroll 1
             for (int it0 = NPRE; it0 < S::ITERS; it0 += PT_BATCH) {
                 float4 buf[PT_BATCH];
@@ -166,7 +149,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         } else {
 #pragma unroll 2
             for (int it = 0; it < S::ITERS; ++it) {
-                const long long i0 = Beven + 2LL * (tid + it * PT_THREADS);   // logical index of the pair's first sample
+                const long long i0 = B + 2LL * (tid + it * PT_THREADS);
                 const float2 a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : make_float2(0.f, 0.f))
                                            : ((Hm1 + i0 >= 0) ? __ldg(hist + (Hm1 + i0)) : make_float2(0.f, 0.f));
                 const long long i1 = i0 + 1;
@@ -177,47 +160,61 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         }
         __syncthreads();
 
-        // ---- prefetch the first batches of this CTA's next tile; they stay in registers across the compute phase
+        // ---- prefetch the first batch of this CTA's next tile; it stays in registers across the compute phase
         if constexpr (!EDGE) {
             const long long nidx = widx + gridDim.x;
             if (nidx < n_work) {
-                const long long Bev = first_input(tile_of(nidx)) & ~1LL;
-                const float4* x4n = reinterpret_cast<const float4*>(x + Bev) + tid;
+                const float4* x4n = reinterpret_cast<const float4*>(x + (P.off + tile_of(nidx) * (long long)(TS * D))) + tid;
 #pragma unroll
                 for (int k = 0; k < NPRE; ++k) pre[k] = __ldcs(x4n + k * PT_THREADS);
             }
         }
 
-        // ---- compute: R outputs per thread, sliding register window per polyphase branch
+        // ---- compute: walk the window positions; every position feeds all outputs it overlaps
         float2 acc[PT_R];
 #pragma unroll
         for (int r = 0; r < PT_R; ++r) acc[r] = make_float2(0.f, 0.f);
-        const float2* sbase = smem + tid * (PT_R + 2);    // pad_idx(tid*8) = tid*10
-#pragma unroll
-        for (int p = 0; p < D; ++p) {
-            const float2* sp = sbase + p * S::JP;
-            float2 w[PT_R];
-#pragma unroll
-            for (int r = 0; r < PT_R; r += 2) {
-                float4 v = *reinterpret_cast<const float4*>(sp + r);
-                w[r] = make_float2(v.x, v.y);
-                w[r + 1] = make_float2(v.z, v.w);
+        const float2* tb = smem + tid * (S::RD + 2);
+        static_for<0, PT_R + Q>([&](auto jc) {
+            constexpr int j = decltype(jc)::value;
+            // samples X[B + (tid*R + j)*D + p], p < D: padded offset j*D + p + 2*floor((j*D + p)/RD)
+            float2 xs[D];
+            constexpr int e0 = j * D;
+            if constexpr (j == PT_R + Q - 1) {
+                xs[0] = tb[S::pad(e0)];                            // the last position only feeds tap Q*D (p = 0)
+            } else {
+                static_for<0, D>([&](auto pc) {
+                    constexpr int pp = decltype(pc)::value;
+                    constexpr int e = e0 + pp;
+                    if constexpr ((e & 1) && pp >= 1) {
+                        // already loaded as the upper half of a 128-bit pair
+                    } else if constexpr (!(e & 1) && pp + 1 < D) {
+                        const float4 v = *reinterpret_cast<const float4*>(tb + S::pad(e));
+                        xs[pp] = make_float2(v.x, v.y);
+                        xs[pp + 1] = make_float2(v.z, v.w);
+                    } else {
+                        xs[pp] = tb[S::pad(e)];
+                    }
+                });
             }
-            float2 nx0 = make_float2(0.f, 0.f), nx1 = nx0;
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-                if ((q & 1) == 0 && q + 1 < Q) {
-                    // elements R+q and R+q+1 of this thread's branch window (contiguous in the padded layout)
-                    float4 v = *reinterpret_cast<const float4*>(sp + pad_idx(PT_R + q));
-                    nx0 = make_float2(v.x, v.y);
-                    nx1 = make_float2(v.z, v.w);
+            static_for<0, PT_R>([&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                constexpr int qq = j - r;
+                if constexpr (qq >= 0 && qq <= Q) {
+                    static_for<0, D>([&](auto pc) {
+                        constexpr int pp = decltype(pc)::value;
+                        if constexpr (qq * D + pp < S::T) {
+                            const float h = P.hr[qq * D + pp];
+                            acc[r] = __ffma2_rn(xs[pp], make_float2(h, h), acc[r]);
+                        }
+                    });
                 }
-                const float h = P.hr[q * D + p];
+            });
+        });
+        if constexpr (ROT) {
+            const float2 Pt = phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B));
 #pragma unroll
-                for (int r = 0; r < PT_R; ++r)
-                    acc[r] = __ffma2_rn(w[(r + q) % PT_R], make_float2(h, h), acc[r]);
-                w[q % PT_R] = (q & 1) ? nx1 : nx0;
-            }
+            for (int r = 0; r < PT_R; ++r) acc[r] = cmul(acc[r], Pt);
         }
 
         const long long mbase = m0 + (long long)tid * PT_R;     // output index of acc[0]
@@ -237,7 +234,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
             __syncthreads();                               // shared tile is reused by the next iteration
         } else {
             // ---- fused FrequencyDiscriminator (frequencydiscriminator.lua:68-88):
-            //      d[m] = atan2(im, re of y[m] * conj(y[m-1])) * (1/gain);  slot 0 of the tile is y[m0] with m0 = first disc output - 1
+            //      d[m] = atan2(im, re of y[m] * conj(y[m-1])) * (1/gain); slot 0 only supplies y[m-1] for slot 1
             float* yd = reinterpret_cast<float*>(yv);
             float2 left;                                   // y just before acc[0]
             left.x = __shfl_up_sync(0xffffffffu, acc[PT_R - 1].x, 1);
@@ -246,19 +243,19 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
             __syncthreads();                               // also fences the shared tile for the next iteration
             if (lane == 0 && warp > 0) left = s_edge[warp - 1];
             if (tid == 0 && tile == 0) acc[0] = __ldg(prev_in);   // stream state: the previous call's last output
+            const long long m_end = m0 + TS + 1;           // outputs >= m_end belong to the next tile
 #pragma unroll
             for (int r = 0; r < PT_R; ++r) {
-                const long long m = mbase + r;             // acc[r] = y[m]; it yields d[m] unless it is the tile's slot 0
+                const long long m = mbase + r;             // acc[r] = y[m]
                 const float2 cur = acc[r];
                 const float2 pv = (r == 0) ? left : acc[r - 1];
-                if (!(tid == 0 && r == 0) && m < n_out) {
+                if (!(tid == 0 && r == 0) && m < m_end && m < n_out) {
                     const float re = fmaf(cur.x, pv.x, cur.y * pv.y);
                     const float im = fmaf(cur.y, pv.x, -cur.x * pv.y);
                     yd[m] = atan2f(im, re) * inv_gain;
+                    if (m == n_out - 1) *prev_out = cur;   // carried to the next call
                 }
-                if (m == n_out - 1) *prev_out = cur;       // carried to the next call
             }
-            // (s_edge is rewritten only after the next iteration's staging barrier)
         }
         if constexpr (EDGE) break;
         widx += gridDim.x;
@@ -266,11 +263,11 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
 }
 
 template <int D, int Q, bool ROT, bool DISC>
-int launch_shape(const PolyParams& P, const float2* x, const float2* hist, long long n, void* y, long long first,
-                 long long n_out, const float2* prev_in, float2* prev_out, float inv_gain, cudaStream_t s) {
+int launch_shape(PolyParams P, const float* hr_base, const float2* E, const float2* x, const float2* hist, long long n,
+                 void* y, long long first, long long n_out, const float2* prev_in, float2* prev_out, float inv_gain,
+                 cudaStream_t s) {
     using S = PolyShape<D, Q>;
-    static_assert(Q * D <= PT_MAXTAPS, "taps table too small");
-    static_assert(S::ITERS <= PT_MAXIT, "step table too small");
+    static_assert(S::T <= PT_MAXTAPS, "taps table too small");
     static bool configured = false;
     static int ctas_per_sm = 1;
     auto kern_i = polyphase_crcf_kernel<D, Q, ROT, DISC, false>;
@@ -282,19 +279,24 @@ int launch_shape(const PolyParams& P, const float2* x, const float2* hist, long 
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = true;
     }
-    constexpr int TS = DISC ? PT_TO - 1 : PT_TO;
-    // DISC: tile t yields discriminator outputs [t*TS, t*TS + TS); its slot 0 is output t*TS - 1
+    constexpr int TS = TileStride<DISC>::TS;
+    // B(tile) = first + m0*D - (Q*D - 1) - shift, m0 = tile*TS - (DISC ? 1 : 0); shift in {0,1} makes it even
+    long long off = first - (DISC ? D : 0) - (long long)(Q * D - 1);
+    const int shift = (int)(((off % 2) + 2) % 2);
+    off -= shift;
+    P.off = off;
+    // hr'[i'] = hr[i' - shift] (hr_base has Q*D entries): one spare zero tap at either end
+    for (int i = 0; i < PT_MAXTAPS; ++i) {
+        const int k = i - shift;
+        P.hr[i] = (k >= 0 && k < Q * D) ? hr_base[k] : 0.0f;
+    }
     const long long tiles = (n_out + TS - 1) / TS;
-    // interior tiles: staged span [Beven, Beven + 2*ITERS*THREADS) inside [0, n), x 16-byte aligned
+    // interior tiles: every staged sample B(t) .. B(t)+LOADED-1 inside [0, n) and x 16-byte aligned
     long long t_lo = 0, t_hi = 0;
     if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-        const long long span = 2LL * S::ITERS * PT_THREADS;
         const long long step = (long long)TS * D;
-        const long long off = first - (DISC ? D : 0) - (long long)(Q * D - 1);   // B(t) = off + t*step
-        // Beven >= B - 1 >= 0   and   B + span <= n
-        const long long need_lo = 1 - off;
-        t_lo = need_lo <= 0 ? 0 : (need_lo + step - 1) / step;
-        const long long lim = n - span - off;
+        t_lo = off >= 0 ? 0 : (-off + step - 1) / step;
+        const long long lim = n - (long long)S::LOADED - off;
         t_hi = lim < 0 ? 0 : lim / step + 1;
         if (t_hi > tiles) t_hi = tiles;
         if (t_lo > t_hi) t_lo = t_hi;
@@ -303,11 +305,11 @@ int launch_shape(const PolyParams& P, const float2* x, const float2* hist, long 
     if (n_int > 0) {
         long long grid = (long long)ctx().sm_count * ctas_per_sm;
         if (grid > n_int) grid = n_int;
-        kern_i<<<(unsigned)grid, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, first, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
+        kern_i<<<(unsigned)grid, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, E, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();
     }
     if (n_edge > 0) {
-        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, first, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
+        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, E, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();
     }
     LRB_CHECK(cudaGetLastError());
@@ -318,7 +320,9 @@ int launch_shape(const PolyParams& P, const float2* x, const float2* hist, long 
 
 struct PolyTaps {
     int M, D, Q;
-    PolyParams P;
+    float hr[PT_MAXTAPS];        // reversed taps, Q*D entries: hr[i'] = h[Q*D-1-i']
+    uint64_t turns_fix;
+    float2* d_E = nullptr;       // tile-relative phasor table (device), when a translator is fused
 };
 
 static int shape_q(int M, int D) {
@@ -330,39 +334,53 @@ static int shape_q(int M, int D) {
     return 0;
 }
 
-PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample) {
+static constexpr int PT_E_LEN = 2 * 48 * PT_THREADS;   // >= LOADED of every instantiated shape
+
+PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table) {
     int Q = shape_q(M, D);
     if (!Q) return nullptr;
     PolyTaps* p = new (std::nothrow) PolyTaps();
     if (!p) return nullptr;
     p->M = M; p->D = D; p->Q = Q;
-    std::memset(&p->P, 0, sizeof(p->P));
     // hr[i'] multiplies X[c - (Q*D-1) + i']  =>  hr[i'] = h[Q*D-1-i'] (zero for tap index >= M)
-    for (int i = 0; i < Q * D; ++i) {
+    for (int i = 0; i < PT_MAXTAPS; ++i) {
         int k = Q * D - 1 - i;
-        p->P.hr[i] = (k < M) ? taps[k] : 0.0f;
+        p->hr[i] = (i < Q * D && k < M) ? taps[k] : 0.0f;
     }
-    p->P.M = M;
-    const double two_pi = 6.283185307179586476925286766559;
-    p->P.turns_fix = turns_to_fix(turns_per_sample);
-    // staging-step phasors from the SAME fixed-point turns the kernel uses for the absolute phase
-    const double tq = std::ldexp((double)p->P.turns_fix, -64);
-    for (int it = 0; it < PT_MAXIT; ++it) {
-        double a = tq * (double)(2 * PT_THREADS) * (double)it;
-        a -= std::floor(a);
-        p->P.step[it] = make_float2((float)std::cos(two_pi * a), (float)std::sin(two_pi * a));
+    p->turns_fix = turns_to_fix(turns_per_sample);
+    if (phasor_table) {
+        // E[i] = exp(j 2 pi turns i) from the SAME fixed-point turns the kernel uses for the tile phasor
+        std::vector<float2> E(PT_E_LEN);
+        const double two_pi = 6.283185307179586476925286766559;
+        const long double tq = ldexpl((long double)p->turns_fix, -64);
+        for (int i = 0; i < PT_E_LEN; ++i) {
+            long double a = tq * (long double)i;
+            a -= floorl(a);
+            E[i] = make_float2((float)std::cos(two_pi * (double)a), (float)std::sin(two_pi * (double)a));
+        }
+        if (cudaMalloc(&p->d_E, sizeof(float2) * PT_E_LEN) != cudaSuccess ||
+            cudaMemcpy(p->d_E, E.data(), sizeof(float2) * PT_E_LEN, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(p->d_E);
+            delete p;
+            set_error("tuner: cannot allocate the phasor table");
+            return nullptr;
+        }
     }
-    p->P.rot1 = make_float2((float)std::cos(two_pi * tq), (float)std::sin(two_pi * tq));
     return p;
 }
 
-void polyphase_release(PolyTaps* p) { delete p; }
+void polyphase_release(PolyTaps* p) {
+    if (!p) return;
+    cudaFree(p->d_E);
+    delete p;
+}
 
-#define LRB_SHAPE(DD, QQ)                                                                                        \
-    if (p->D == DD && p->Q == QQ) {                                                                              \
-        if (disc) return launch_shape<DD, QQ, true, true>(P, x, hist, n, y, first, n_out, prev_in, prev_out, inv_gain, s); \
-        return rotate ? launch_shape<DD, QQ, true, false>(P, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s)    \
-                      : launch_shape<DD, QQ, false, false>(P, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);  \
+#define LRB_SHAPE(DD, QQ)                                                                                              \
+    if (p->D == DD && p->Q == QQ) {                                                                                    \
+        static_assert(PolyShape<DD, QQ>::LOADED <= PT_E_LEN, "phasor table too short");                                \
+        if (disc) return launch_shape<DD, QQ, true, true>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, prev_in, prev_out, inv_gain, s); \
+        return rot ? launch_shape<DD, QQ, true, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s)    \
+                   : launch_shape<DD, QQ, false, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);  \
     }
 
 static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2* hist, long long n, void* y,
@@ -370,8 +388,17 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
                                 const float2* prev_in, float2* prev_out, float inv_gain, cudaStream_t s) {
     if (!p) return 0;
     if (n_out <= 0) return 1;
-    PolyParams P = p->P;
+    const bool rot = rotate && p->d_E != nullptr;
+    if (disc && !rot) {
+        // the fused discriminator is instantiated together with the translator; a zero offset gets the all-ones table
+        set_error("tuner: discriminator fusion needs the translator path");
+        return -1;
+    }
+    PolyParams P;
+    std::memset(&P, 0, sizeof(P));
+    P.turns_fix = p->turns_fix;
     P.g0 = g0;
+    P.M = p->M;
     LRB_SHAPE(1, 16) LRB_SHAPE(1, 32)
     LRB_SHAPE(2, 32) LRB_SHAPE(2, 64)
     LRB_SHAPE(3, 22) LRB_SHAPE(3, 43)
@@ -458,7 +485,7 @@ struct TunerBlock : Block {
 };
 
 Block* make_tuner(double turns_per_sample, const float* taps, int ntaps, int decim, float disc_gain) {
-    PolyTaps* p = polyphase_prepare(taps, ntaps, decim, turns_per_sample);
+    PolyTaps* p = polyphase_prepare(taps, ntaps, decim, turns_per_sample, true);
     if (!p) return nullptr;      // unsupported shape: the graph keeps the blocks separate
     TunerBlock* t = new (std::nothrow) TunerBlock(p, disc_gain);
     if (!t) { polyphase_release(p); set_error("out of memory"); return nullptr; }
