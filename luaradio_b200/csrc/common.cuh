@@ -97,6 +97,28 @@ __device__ __forceinline__ float2 phasor_from_fix(uint64_t ph) {
     sincospif(half_turns, &s, &c);
     return make_float2(c, s);
 }
+// atan2 for the fused discriminator epilogue: one fast division, a degree-8 polynomial in a^2 on [0, 1]
+// (max abs error 1.1e-7 rad, fitted and checked in float32) and three selects -- about 25 instructions instead
+// of the ~110 of atan2f, whose 8 calls per thread made up a third of the tuner kernel's instruction stream.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;
+    const float z = a * a;
+    float r = 0.0028340641874819994f;
+    r = fmaf(r, z, -0.016005029901862144f);
+    r = fmaf(r, z, 0.042587608098983765f);
+    r = fmaf(r, z, -0.07495445758104324f);
+    r = fmaf(r, z, 0.10636754333972931f);
+    r = fmaf(r, z, -0.14202570915222168f);
+    r = fmaf(r, z, 0.19992484152317047f);
+    r = fmaf(r, z, -0.3333306610584259f);
+    r = fmaf(r, z, 1.0f);
+    r *= a;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = x < 0.f ? 3.14159265358979324f - r : r;
+    return copysignf(r, y);
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     // (a.x + j a.y)(b.x + j b.y): FMUL2 + FFMA2 with the .LO_HI.NP operand swizzle on sm_100
     float2 t = __fmul2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y));

@@ -53,7 +53,9 @@ __device__ __forceinline__ float2 ld_cg(const float2* p) { return __ldcg(p); }
 constexpr int IIR_WARM = 512;
 constexpr int IIR_PAY = IIR_THREADS * IIR_V - IIR_WARM;   // payload samples per CTA after the first
 
-template <typename T, bool LOCAL>
+// NBT: compile-time number of feed-forward taps (2 for every single-pole design of the reference; IIR_MAX_NB = generic).
+// With the generic 9-slot loops the kernel was instruction-bound (ncu: 74 % issue-active, ~70 instr per sample).
+template <typename T, bool LOCAL, int NBT>
 __global__ void __launch_bounds__(IIR_THREADS)
 iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirParams P,
                  const T* __restrict__ xhist_in, T* __restrict__ xhist_out,
@@ -66,8 +68,14 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     int tile;
     long long span0;                                  // first sample index of this CTA's span
     long long pay0;                                   // first sample index this CTA stores
+    // LOCAL: persistent CTAs, grid-stride over the tiles (`epoch` carries the tile count): 15 000 short-lived
+    // 4096-sample CTAs spent most of their life in launch/drain latency
+    int tile_iter = blockIdx.x;
+    T xnext[IIR_V + NBT - 1];                         // LOCAL: next tile's inputs, fetched while this tile is scanned
+    bool have_next = false;
+next_tile:
     if constexpr (LOCAL) {
-        tile = blockIdx.x;
+        tile = tile_iter;
         pay0 = tile == 0 ? 0 : (long long)IIR_TILE + (long long)(tile - 1) * IIR_PAY;
         span0 = tile == 0 ? 0 : pay0 - IIR_WARM;
     } else {
@@ -80,25 +88,50 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     const int nh = P.nb - 1;
 
     // ---- u[i] = sum_j b[j] x[i-j] over this thread's V samples (zero beyond n)
-    T xv[IIR_V + IIR_MAX_NB - 1];
+    T xv[IIR_V + NBT - 1];
+    if (LOCAL && have_next) {
 #pragma unroll
-    for (int i = 0; i < IIR_V + IIR_MAX_NB - 1; ++i) {
-        long long idx = base + i - (IIR_MAX_NB - 1);
-        T v = zero_of(T());
-        if (i >= IIR_MAX_NB - 1 - nh) {
-            if (idx >= 0) { if (idx < n) v = __ldg(x + idx); }
-            else if (nh + idx >= 0) v = __ldg(xhist_in + (nh + idx));
+        for (int i = 0; i < IIR_V + NBT - 1; ++i) xv[i] = xnext[i];
+    } else if (base >= NBT - 1 && base + IIR_V <= n) {
+        // interior thread: no bounds checks
+        const T* xb = x + (base - (NBT - 1));
+#pragma unroll
+        for (int i = 0; i < IIR_V + NBT - 1; ++i) xv[i] = __ldg(xb + i);
+    } else {
+#pragma unroll
+        for (int i = 0; i < IIR_V + NBT - 1; ++i) {
+            long long idx = base + i - (NBT - 1);
+            T v = zero_of(T());
+            if (i >= NBT - 1 - nh) {
+                if (idx >= 0) { if (idx < n) v = __ldg(x + idx); }
+                else if (nh + idx >= 0) v = __ldg(xhist_in + (nh + idx));
+            }
+            xv[i] = v;
         }
-        xv[i] = v;
     }
     T yl[IIR_V];
 #pragma unroll
     for (int i = 0; i < IIR_V; ++i) {
         T u = zero_of(T());
 #pragma unroll
-        for (int j = 0; j < IIR_MAX_NB; ++j)
-            if (j < P.nb) u = fmas(P.b[j], xv[i + IIR_MAX_NB - 1 - j], u);
+        for (int j = 0; j < NBT; ++j)
+            if (NBT < IIR_MAX_NB || j < P.nb) u = fmas(P.b[j], xv[i + NBT - 1 - j], u);
         yl[i] = (i == 0) ? u : fmas(P.c, yl[i - 1], u);
+    }
+
+    if constexpr (LOCAL) {
+        // prefetch the inputs of this CTA's next tile (interior threads only; the rest reload with bounds checks)
+        have_next = false;
+        const int nt = tile_iter + gridDim.x;
+        if (nt < (int)epoch) {
+            const long long nb0 = (long long)IIR_TILE + (long long)(nt - 1) * IIR_PAY - IIR_WARM + (long long)tid * IIR_V;
+            if (nb0 >= NBT - 1 && nb0 + IIR_V <= n) {
+                const T* xb = x + (nb0 - (NBT - 1));
+#pragma unroll
+                for (int i = 0; i < IIR_V + NBT - 1; ++i) xnext[i] = __ldg(xb + i);
+                have_next = true;
+            }
+        }
     }
 
     // ---- warp scan of the per-thread zero-state end values
@@ -222,6 +255,10 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
         long long i = n - nh + tid;
         xhist_out[tid] = (i >= 0) ? x[i] : xhist_in[nh + i];
     }
+    if constexpr (LOCAL) {
+        tile_iter += gridDim.x;
+        if (tile_iter < (int)epoch) goto next_tile;   // (the three barriers of the next pass order the shared scratch)
+    }
 }
 
 }  // namespace
@@ -260,14 +297,14 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
     const bool local = std::pow(std::fabs(cd), (double)IIR_WARM) < 1e-12;
     if (local) {
         int tiles = n <= IIR_TILE ? 1 : 1 + (int)((n - IIR_TILE + IIR_PAY - 1) / IIR_PAY);
-        if (complex_data)
-            iir1_scan_kernel<float2, true><<<tiles, IIR_THREADS, 0, s>>>((const float2*)x, n, (float2*)y, P,
-                (const float2*)xhist_in, (float2*)xhist_out, (const float2*)ystate_in, (float2*)ystate_out,
-                first, D, nullptr, nullptr, nullptr, nullptr, 0u);
-        else
-            iir1_scan_kernel<float, true><<<tiles, IIR_THREADS, 0, s>>>((const float*)x, n, (float*)y, P,
-                (const float*)xhist_in, (float*)xhist_out, (const float*)ystate_in, (float*)ystate_out,
-                first, D, nullptr, nullptr, nullptr, nullptr, 0u);
+        int grid = ctx().sm_count * 2;
+        if (grid > tiles) grid = tiles;
+#define LRB_IIR_LOCAL(TT, NN)                                                                                   \
+        iir1_scan_kernel<TT, true, NN><<<grid, IIR_THREADS, 0, s>>>((const TT*)x, n, (TT*)y, P, (const TT*)xhist_in, \
+            (TT*)xhist_out, (const TT*)ystate_in, (TT*)ystate_out, first, D, nullptr, nullptr, nullptr, nullptr, (unsigned)tiles)
+        if (complex_data) { if (nb == 2) LRB_IIR_LOCAL(float2, 2); else LRB_IIR_LOCAL(float2, IIR_MAX_NB); }
+        else { if (nb == 2) LRB_IIR_LOCAL(float, 2); else LRB_IIR_LOCAL(float, IIR_MAX_NB); }
+#undef LRB_IIR_LOCAL
         count_launch();
         LRB_CHECK(cudaGetLastError());
         return 0;
@@ -279,14 +316,12 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
     }
     LRB_CHECK(cudaMemsetAsync(w->ticket, 0, sizeof(int), s));
     int tiles = (int)((n + IIR_TILE - 1) / IIR_TILE);
-    if (complex_data)
-        iir1_scan_kernel<float2, false><<<tiles, IIR_THREADS, 0, s>>>((const float2*)x, n, (float2*)y, P,
-            (const float2*)xhist_in, (float2*)xhist_out, (const float2*)ystate_in, (float2*)ystate_out,
-            first, D, w->ticket, w->flags, (float2*)w->agg, (float2*)w->pfx, w->epoch);
-    else
-        iir1_scan_kernel<float, false><<<tiles, IIR_THREADS, 0, s>>>((const float*)x, n, (float*)y, P,
-            (const float*)xhist_in, (float*)xhist_out, (const float*)ystate_in, (float*)ystate_out,
-            first, D, w->ticket, w->flags, (float*)w->agg, (float*)w->pfx, w->epoch);
+#define LRB_IIR_SCAN(TT, NN)                                                                                    \
+    iir1_scan_kernel<TT, false, NN><<<tiles, IIR_THREADS, 0, s>>>((const TT*)x, n, (TT*)y, P, (const TT*)xhist_in,  \
+        (TT*)xhist_out, (const TT*)ystate_in, (TT*)ystate_out, first, D, w->ticket, w->flags, (TT*)w->agg, (TT*)w->pfx, w->epoch)
+    if (complex_data) { if (nb == 2) LRB_IIR_SCAN(float2, 2); else LRB_IIR_SCAN(float2, IIR_MAX_NB); }
+    else { if (nb == 2) LRB_IIR_SCAN(float, 2); else LRB_IIR_SCAN(float, IIR_MAX_NB); }
+#undef LRB_IIR_SCAN
     count_launch();
     LRB_CHECK(cudaGetLastError());
     return 0;

@@ -122,29 +122,38 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         const long long m0 = tile * TS - (DISC ? 1 : 0);             // output index of slot 0
 
         // ---- stage: global -> (x E) -> shared, natural order
-        auto stage_pair = [&](float4 v, int it) {
+        auto stage_pair = [&](float4 v, float4 e, int it) {
             const int u = tid + it * PT_THREADS;
             float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
             if constexpr (ROT) {
-                const float4 e = __ldg(reinterpret_cast<const float4*>(E) + u);
                 a = cmul(a, make_float2(e.x, e.y));
                 b = cmul(b, make_float2(e.z, e.w));
             }
             *reinterpret_cast<float4*>(smem + S::pad(2 * u)) = make_float4(a.x, a.y, b.x, b.y);
         };
+        const float4* E4 = reinterpret_cast<const float4*>(E) + tid;
         if constexpr (!EDGE) {
+            {
+                // first batch: x was prefetched during the previous tile's compute phase; fetch its phasors together
+                float4 be[NPRE];
 #pragma unroll
-            for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], k);
+                for (int k = 0; k < NPRE; ++k) be[k] = ROT ? __ldg(E4 + k * PT_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], be[k], k);
+            }
             const float4* x4 = reinterpret_cast<const float4*>(x + B) + tid;
 #pragma unroll 1
             for (int it0 = NPRE; it0 < S::ITERS; it0 += PT_BATCH) {
-                float4 buf[PT_BATCH];
+                float4 buf[PT_BATCH], be[PT_BATCH];
 #pragma unroll
                 for (int k = 0; k < PT_BATCH; ++k)
-                    if (it0 + k < S::ITERS) buf[k] = __ldcs(x4 + (it0 + k) * PT_THREADS);
+                    if (it0 + k < S::ITERS) {
+                        buf[k] = __ldcs(x4 + (it0 + k) * PT_THREADS);
+                        be[k] = ROT ? __ldg(E4 + (it0 + k) * PT_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
                 for (int k = 0; k < PT_BATCH; ++k)
-                    if (it0 + k < S::ITERS) stage_pair(buf[k], it0 + k);
+                    if (it0 + k < S::ITERS) stage_pair(buf[k], be[k], it0 + k);
             }
         } else {
 #pragma unroll 2
@@ -155,7 +164,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 const long long i1 = i0 + 1;
                 const float2 b = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : make_float2(0.f, 0.f))
                                            : ((Hm1 + i1 >= 0) ? __ldg(hist + (Hm1 + i1)) : make_float2(0.f, 0.f));
-                stage_pair(make_float4(a.x, a.y, b.x, b.y), it);
+                stage_pair(make_float4(a.x, a.y, b.x, b.y), ROT ? __ldg(E4 + it * PT_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f), it);
             }
         }
         __syncthreads();
@@ -252,7 +261,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 if (!(tid == 0 && r == 0) && m < m_end && m < n_out) {
                     const float re = fmaf(cur.x, pv.x, cur.y * pv.y);
                     const float im = fmaf(cur.y, pv.x, -cur.x * pv.y);
-                    yd[m] = atan2f(im, re) * inv_gain;
+                    yd[m] = fast_atan2f(im, re) * inv_gain;
                     if (m == n_out - 1) *prev_out = cur;   // carried to the next call
                 }
             }
