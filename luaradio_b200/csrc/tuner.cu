@@ -50,8 +50,10 @@ constexpr int PT_TO = PT_THREADS * PT_R;     // filter outputs per tile
 constexpr int PT_MAXTAPS = 144;              // Q*D + 1 upper bound for the instantiated shapes
 constexpr int PT_BATCH = 7;                  // 128-bit loads issued back to back per staging batch
 
+constexpr int PT_MAXIT = 48;                 // staging iterations (pairs per thread) upper bound
 struct PolyParams {
     float hr[PT_MAXTAPS];        // reversed taps with the launch's alignment shift, zero padded to Q*D + 1
+    float2 step[PT_MAXIT];       // exp(j*2*pi*turns * 2*PT_THREADS*it): phasor advance of staging iteration `it`
     uint64_t turns_fix;          // turns per sample, 2^-64 units
     uint64_t g0;                 // global index of x[0]
     long long off;               // B(tile) = off + tile * TS * D   (even)
@@ -94,12 +96,20 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                       const float2* __restrict__ prev_in, float2* __restrict__ prev_out, float inv_gain) {
     using S = PolyShape<D, Q>;
     constexpr int TS = TileStride<DISC>::TS;
-    constexpr int NPRE = S::ITERS < PT_BATCH ? S::ITERS : PT_BATCH;
+    constexpr int NPRE = S::ITERS < 2 * PT_BATCH ? S::ITERS : 2 * PT_BATCH;   // pairs prefetched across the compute phase
     extern __shared__ __align__(16) float2 smem[];
     __shared__ float2 s_edge[PT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int Hm1 = P.M - 1;
 
+    // tile-relative phasors of this thread's first sample pair, E[2 tid] and E[2 tid + 1]; the pair of staging
+    // iteration `it` is 2*PT_THREADS*it samples later: E[2u] = A0 * step[it].  (A phasor TABLE in global memory
+    // cost one more load stream whose latency was exposed three times per tile -- 42 % of all stall samples.)
+    float2 A0 = make_float2(1.f, 0.f), A1 = make_float2(1.f, 0.f);
+    if constexpr (ROT) {
+        A0 = phasor_from_fix(P.turns_fix * (uint64_t)(2 * tid));
+        A1 = phasor_from_fix(P.turns_fix * (uint64_t)(2 * tid + 1));
+    }
     auto tile_of = [&](long long idx) -> long long { return EDGE ? (idx < t_lo ? idx : t_hi + (idx - t_lo)) : (t_lo + idx); };
     const long long n_work = EDGE ? 0 : (t_hi - t_lo);
     long long widx = blockIdx.x;
@@ -122,38 +132,37 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         const long long m0 = tile * TS - (DISC ? 1 : 0);             // output index of slot 0
 
         // ---- stage: global -> (x E) -> shared, natural order
-        auto stage_pair = [&](float4 v, float4 e, int it) {
+        auto stage_pair = [&](float4 v, int it) {
             const int u = tid + it * PT_THREADS;
             float2 a = make_float2(v.x, v.y), b = make_float2(v.z, v.w);
             if constexpr (ROT) {
-                a = cmul(a, make_float2(e.x, e.y));
-                b = cmul(b, make_float2(e.z, e.w));
+                const float2 st = P.step[it];
+                a = cmul(a, cmul(A0, st));
+                b = cmul(b, cmul(A1, st));
             }
             *reinterpret_cast<float4*>(smem + S::pad(2 * u)) = make_float4(a.x, a.y, b.x, b.y);
         };
-        const float4* E4 = reinterpret_cast<const float4*>(E) + tid;
         if constexpr (!EDGE) {
-            {
-                // first batch: x was prefetched during the previous tile's compute phase; fetch its phasors together
-                float4 be[NPRE];
-#pragma unroll
-                for (int k = 0; k < NPRE; ++k) be[k] = ROT ? __ldg(E4 + k * PT_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], be[k], k);
-            }
+            // the first NPRE pairs were prefetched during the previous tile's compute phase; the rest of the tile
+            // is requested now and lands while those are rotated and stored
             const float4* x4 = reinterpret_cast<const float4*>(x + B) + tid;
+            constexpr int REST = (S::ITERS - NPRE) < PT_BATCH ? (S::ITERS - NPRE) : PT_BATCH;
+            float4 rest[REST > 0 ? REST : 1];
+#pragma unroll
+            for (int k = 0; k < REST; ++k) rest[k] = __ldcs(x4 + (NPRE + k) * PT_THREADS);
+#pragma unroll
+            for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], k);
+#pragma unroll
+            for (int k = 0; k < REST; ++k) stage_pair(rest[k], NPRE + k);
 #pragma unroll 1
-            for (int it0 = NPRE; it0 < S::ITERS; it0 += PT_BATCH) {
-                float4 buf[PT_BATCH], be[PT_BATCH];
+            for (int it0 = NPRE + REST; it0 < S::ITERS; it0 += PT_BATCH) {
+                float4 buf[PT_BATCH];
 #pragma unroll
                 for (int k = 0; k < PT_BATCH; ++k)
-                    if (it0 + k < S::ITERS) {
-                        buf[k] = __ldcs(x4 + (it0 + k) * PT_THREADS);
-                        be[k] = ROT ? __ldg(E4 + (it0 + k) * PT_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
+                    if (it0 + k < S::ITERS) buf[k] = __ldcs(x4 + (it0 + k) * PT_THREADS);
 #pragma unroll
                 for (int k = 0; k < PT_BATCH; ++k)
-                    if (it0 + k < S::ITERS) stage_pair(buf[k], be[k], it0 + k);
+                    if (it0 + k < S::ITERS) stage_pair(buf[k], it0 + k);
             }
         } else {
 #pragma unroll 2
@@ -164,7 +173,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 const long long i1 = i0 + 1;
                 const float2 b = (i1 >= 0) ? (i1 < n ? __ldg(x + i1) : make_float2(0.f, 0.f))
                                            : ((Hm1 + i1 >= 0) ? __ldg(hist + (Hm1 + i1)) : make_float2(0.f, 0.f));
-                stage_pair(make_float4(a.x, a.y, b.x, b.y), ROT ? __ldg(E4 + it * PT_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f), it);
+                stage_pair(make_float4(a.x, a.y, b.x, b.y), it);
             }
         }
         __syncthreads();
@@ -220,7 +229,10 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 }
             });
         });
-        if constexpr (ROT) {
+        // tile phasor: the staged samples carry only the tile-relative rotation E; P_tile = exp(jw(g0 + B)) commutes
+        // with the filter.  The discriminator output y[m] conj(y[m-1]) does not depend on it (|P| = 1), so with DISC
+        // it is only applied to the two samples that cross the call boundary (prev_in / prev_out).
+        if constexpr (ROT && !DISC) {
             const float2 Pt = phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B));
 #pragma unroll
             for (int r = 0; r < PT_R; ++r) acc[r] = cmul(acc[r], Pt);
@@ -251,7 +263,11 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
             if (lane == 31) s_edge[warp] = acc[PT_R - 1];
             __syncthreads();                               // also fences the shared tile for the next iteration
             if (lane == 0 && warp > 0) left = s_edge[warp - 1];
-            if (tid == 0 && tile == 0) acc[0] = __ldg(prev_in);   // stream state: the previous call's last output
+            if (tid == 0 && tile == 0) {
+                // stream state: the previous call's last output (absolute phase) brought into this tile's frame
+                const float2 Pt = ROT ? phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B)) : make_float2(1.f, 0.f);
+                acc[0] = cmul(__ldg(prev_in), make_float2(Pt.x, -Pt.y));
+            }
             const long long m_end = m0 + TS + 1;           // outputs >= m_end belong to the next tile
 #pragma unroll
             for (int r = 0; r < PT_R; ++r) {
@@ -262,7 +278,10 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                     const float re = fmaf(cur.x, pv.x, cur.y * pv.y);
                     const float im = fmaf(cur.y, pv.x, -cur.x * pv.y);
                     yd[m] = fast_atan2f(im, re) * inv_gain;
-                    if (m == n_out - 1) *prev_out = cur;   // carried to the next call
+                    if (m == n_out - 1) {                   // carried to the next call, in absolute phase
+                        const float2 Pt = ROT ? phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B)) : make_float2(1.f, 0.f);
+                        *prev_out = cmul(cur, Pt);
+                    }
                 }
             }
         }
@@ -331,7 +350,9 @@ struct PolyTaps {
     int M, D, Q;
     float hr[PT_MAXTAPS];        // reversed taps, Q*D entries: hr[i'] = h[Q*D-1-i']
     uint64_t turns_fix;
-    float2* d_E = nullptr;       // tile-relative phasor table (device), when a translator is fused
+    float2 step[PT_MAXIT];       // per-staging-iteration phasor advance (see PolyParams)
+    bool rotates = false;        // a translator is fused
+    float2* d_E = nullptr;       // (unused; kept so the launch signature stays put)
 };
 
 static int shape_q(int M, int D) {
@@ -357,22 +378,15 @@ PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sa
         p->hr[i] = (i < Q * D && k < M) ? taps[k] : 0.0f;
     }
     p->turns_fix = turns_to_fix(turns_per_sample);
-    if (phasor_table) {
-        // E[i] = exp(j 2 pi turns i) from the SAME fixed-point turns the kernel uses for the tile phasor
-        std::vector<float2> E(PT_E_LEN);
+    p->rotates = phasor_table;
+    {
+        // step[it] = exp(j 2 pi turns * 2*PT_THREADS*it) from the SAME fixed-point turns the kernel uses
         const double two_pi = 6.283185307179586476925286766559;
         const long double tq = ldexpl((long double)p->turns_fix, -64);
-        for (int i = 0; i < PT_E_LEN; ++i) {
-            long double a = tq * (long double)i;
+        for (int it = 0; it < PT_MAXIT; ++it) {
+            long double a = tq * (long double)(2 * PT_THREADS) * (long double)it;
             a -= floorl(a);
-            E[i] = make_float2((float)std::cos(two_pi * (double)a), (float)std::sin(two_pi * (double)a));
-        }
-        if (cudaMalloc(&p->d_E, sizeof(float2) * PT_E_LEN) != cudaSuccess ||
-            cudaMemcpy(p->d_E, E.data(), sizeof(float2) * PT_E_LEN, cudaMemcpyHostToDevice) != cudaSuccess) {
-            cudaFree(p->d_E);
-            delete p;
-            set_error("tuner: cannot allocate the phasor table");
-            return nullptr;
+            p->step[it] = make_float2((float)std::cos(two_pi * (double)a), (float)std::sin(two_pi * (double)a));
         }
     }
     return p;
@@ -386,7 +400,7 @@ void polyphase_release(PolyTaps* p) {
 
 #define LRB_SHAPE(DD, QQ)                                                                                              \
     if (p->D == DD && p->Q == QQ) {                                                                                    \
-        static_assert(PolyShape<DD, QQ>::LOADED <= PT_E_LEN, "phasor table too short");                                \
+        static_assert(PolyShape<DD, QQ>::ITERS <= PT_MAXIT, "step table too short");                                   \
         if (disc) return launch_shape<DD, QQ, true, true>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, prev_in, prev_out, inv_gain, s); \
         return rot ? launch_shape<DD, QQ, true, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s)    \
                    : launch_shape<DD, QQ, false, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);  \
@@ -397,7 +411,7 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
                                 const float2* prev_in, float2* prev_out, float inv_gain, cudaStream_t s) {
     if (!p) return 0;
     if (n_out <= 0) return 1;
-    const bool rot = rotate && p->d_E != nullptr;
+    const bool rot = rotate && p->rotates;
     if (disc && !rot) {
         // the fused discriminator is instantiated together with the translator; a zero offset gets the all-ones table
         set_error("tuner: discriminator fusion needs the translator path");
@@ -406,6 +420,7 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
     PolyParams P;
     std::memset(&P, 0, sizeof(P));
     P.turns_fix = p->turns_fix;
+    std::memcpy(P.step, p->step, sizeof(P.step));
     P.g0 = g0;
     P.M = p->M;
     LRB_SHAPE(1, 16) LRB_SHAPE(1, 32)

@@ -56,6 +56,25 @@ def main():
             except (ValueError, IndexError):
                 pass
         tot = sum(s for s, _ in data) or 1
+        # regions delimited by CTA barriers: cumulative share of stall samples and of executed instructions
+        try:
+            iex = h.index("Instructions Executed")
+            ex = []
+            for r in src[2:]:
+                try:
+                    ex.append(int(r[iex]))
+                except (ValueError, IndexError):
+                    ex.append(0)
+            ex = ex[:len(data)]
+            bars = [i for i, (_, ins) in enumerate(data) if ins.startswith("BAR") or " BAR." in ins]
+            edges = [0] + bars + [len(data)]
+            etot = sum(ex) or 1
+            print("  regions between barriers (instruction index range: %% of stall samples, %% of executed warp instructions):")
+            for a, b in zip(edges[:-1], edges[1:]):
+                if b > a:
+                    print("    [%5d, %5d)  samples %5.1f%%  executed %5.1f%%" % (a, b, 100.0 * sum(x for x, _ in data[a:b]) / tot, 100.0 * sum(ex[a:b]) / etot))
+        except ValueError:
+            pass
         print("  top stall-sample instructions (of %d samples):" % tot)
         for s, ins in sorted(data, reverse=True)[:10]:
             print("    %5.1f%%  %s" % (100.0 * s / tot, ins[:100]))
