@@ -119,6 +119,29 @@ __device__ __forceinline__ float fast_atan2f(float y, float x) {
     r = x < 0.f ? 3.14159265358979324f - r : r;
     return copysignf(r, y);
 }
+// Two atan2 at once on packed f32x2 lanes (y = (y0, y1), x = (x0, x1)): the polynomial and the squares run as
+// FFMA2/FMUL2, only the reciprocal and the selects stay scalar.
+__device__ __forceinline__ float2 fast_atan2f_x2(float2 y, float2 x) {
+    const float ax0 = fabsf(x.x), ay0 = fabsf(y.x), ax1 = fabsf(x.y), ay1 = fabsf(y.y);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    const float2 a = make_float2(mx0 > 0.f ? __fdividef(mn0, mx0) : 0.f, mx1 > 0.f ? __fdividef(mn1, mx1) : 0.f);
+    const float2 z = __fmul2_rn(a, a);
+    float2 r = make_float2(0.0028340641874819994f, 0.0028340641874819994f);
+    r = __ffma2_rn(r, z, make_float2(-0.016005029901862144f, -0.016005029901862144f));
+    r = __ffma2_rn(r, z, make_float2(0.042587608098983765f, 0.042587608098983765f));
+    r = __ffma2_rn(r, z, make_float2(-0.07495445758104324f, -0.07495445758104324f));
+    r = __ffma2_rn(r, z, make_float2(0.10636754333972931f, 0.10636754333972931f));
+    r = __ffma2_rn(r, z, make_float2(-0.14202570915222168f, -0.14202570915222168f));
+    r = __ffma2_rn(r, z, make_float2(0.19992484152317047f, 0.19992484152317047f));
+    r = __ffma2_rn(r, z, make_float2(-0.3333306610584259f, -0.3333306610584259f));
+    r = __ffma2_rn(r, z, make_float2(1.0f, 1.0f));
+    r = __fmul2_rn(r, a);
+    float r0 = ay0 > ax0 ? 1.57079632679489662f - r.x : r.x;
+    float r1 = ay1 > ax1 ? 1.57079632679489662f - r.y : r.y;
+    r0 = x.x < 0.f ? 3.14159265358979324f - r0 : r0;
+    r1 = x.y < 0.f ? 3.14159265358979324f - r1 : r1;
+    return make_float2(copysignf(r0, y.x), copysignf(r1, y.y));
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     // (a.x + j a.y)(b.x + j b.y): FMUL2 + FFMA2 with the .LO_HI.NP operand swizzle on sm_100
     float2 t = __fmul2_rn(make_float2(-a.y, a.x), make_float2(b.y, b.y));

@@ -268,19 +268,32 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 const float2 Pt = ROT ? phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B)) : make_float2(1.f, 0.f);
                 acc[0] = cmul(__ldg(prev_in), make_float2(Pt.x, -Pt.y));
             }
-            const long long m_end = m0 + TS + 1;           // outputs >= m_end belong to the next tile
+            // slots are tile-relative 32-bit indices: slot s holds y[m0 + s]; slots 1 .. lim-1 produce outputs
+            const long long room = n_out - m0;             // > 1 for every launched tile
+            const int lim = room < (long long)(TS + 1) ? (int)room : TS + 1;
+            const int s0 = tid * PT_R;
+            float* yt = yd + m0;
+            // y[m] * conj(y[m-1]) for the 8 slots, two at a time on packed lanes
+            float dout[PT_R];
+#pragma unroll
+            for (int r = 0; r < PT_R; r += 2) {
+                const float2 c0 = acc[r], p0 = (r == 0) ? left : acc[r - 1];
+                const float2 c1 = acc[r + 1], p1 = acc[r];
+                // c * conj(p) = (c.x p.x + c.y p.y,  c.y p.x - c.x p.y)
+                const float2 t0 = __ffma2_rn(c0, make_float2(p0.x, p0.x), __fmul2_rn(make_float2(c0.y, -c0.x), make_float2(p0.y, p0.y)));
+                const float2 t1 = __ffma2_rn(c1, make_float2(p1.x, p1.x), __fmul2_rn(make_float2(c1.y, -c1.x), make_float2(p1.y, p1.y)));
+                const float2 ang = fast_atan2f_x2(make_float2(t0.y, t1.y), make_float2(t0.x, t1.x));
+                dout[r] = ang.x * inv_gain;
+                dout[r + 1] = ang.y * inv_gain;
+            }
 #pragma unroll
             for (int r = 0; r < PT_R; ++r) {
-                const long long m = mbase + r;             // acc[r] = y[m]
-                const float2 cur = acc[r];
-                const float2 pv = (r == 0) ? left : acc[r - 1];
-                if (!(tid == 0 && r == 0) && m < m_end && m < n_out) {
-                    const float re = fmaf(cur.x, pv.x, cur.y * pv.y);
-                    const float im = fmaf(cur.y, pv.x, -cur.x * pv.y);
-                    yd[m] = fast_atan2f(im, re) * inv_gain;
-                    if (m == n_out - 1) {                   // carried to the next call, in absolute phase
+                const int sl = s0 + r;
+                if (sl >= 1 && sl < lim) {
+                    yt[sl] = dout[r];
+                    if ((long long)sl == room - 1) {        // last output of the call: carried to the next one, in absolute phase
                         const float2 Pt = ROT ? phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B)) : make_float2(1.f, 0.f);
-                        *prev_out = cmul(cur, Pt);
+                        *prev_out = cmul(acc[r], Pt);
                     }
                 }
             }
