@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libluaradio_b200.so")
+LIB_PATH = os.environ.get("LRB200_LIB", os.path.join(_HERE, "libluaradio_b200.so"))   # override: A/B-testing kernel builds
 
 LRB200_HOST = 0
 LRB200_DEVICE = 1

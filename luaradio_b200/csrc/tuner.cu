@@ -44,11 +44,18 @@ namespace lrb {
 
 namespace {
 
-constexpr int PT_THREADS = 128;
-constexpr int PT_R = 8;
+#ifndef LRB_PT_THREADS
+#define LRB_PT_THREADS 128
+#define LRB_PT_R 8
+#define LRB_PT_CTAS 4
+#define LRB_PT_PREFETCH 14
+#define LRB_PT_BATCH 7
+#endif
+constexpr int PT_THREADS = LRB_PT_THREADS;
+constexpr int PT_R = LRB_PT_R;
 constexpr int PT_TO = PT_THREADS * PT_R;     // filter outputs per tile
 constexpr int PT_MAXTAPS = 144;              // Q*D + 1 upper bound for the instantiated shapes
-constexpr int PT_BATCH = 7;                  // 128-bit loads issued back to back per staging batch
+constexpr int PT_BATCH = LRB_PT_BATCH;       // 128-bit loads issued back to back per staging batch
 
 constexpr int PT_MAXIT = 48;                 // staging iterations (pairs per thread) upper bound
 struct PolyParams {
@@ -89,14 +96,14 @@ template <bool DISC>
 struct TileStride { static constexpr int TS = DISC ? PT_TO - 2 : PT_TO; };
 
 template <int D, int Q, bool ROT, bool DISC, bool EDGE>
-__global__ void __launch_bounds__(PT_THREADS, 4)
+__global__ void __launch_bounds__(PT_THREADS, LRB_PT_CTAS)
 polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, long long n,
                       void* __restrict__ yv, long long n_out, const __grid_constant__ PolyParams P,
                       const float2* __restrict__ E, long long t_lo, long long t_hi,
                       const float2* __restrict__ prev_in, float2* __restrict__ prev_out, float inv_gain) {
     using S = PolyShape<D, Q>;
     constexpr int TS = TileStride<DISC>::TS;
-    constexpr int NPRE = S::ITERS < 2 * PT_BATCH ? S::ITERS : 2 * PT_BATCH;   // pairs prefetched across the compute phase
+    constexpr int NPRE = S::ITERS < LRB_PT_PREFETCH ? S::ITERS : LRB_PT_PREFETCH;   // pairs prefetched across the compute phase
     extern __shared__ __align__(16) float2 smem[];
     __shared__ float2 s_edge[PT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -368,19 +375,22 @@ struct PolyTaps {
     float2* d_E = nullptr;       // (unused; kept so the launch signature stays put)
 };
 
-static int shape_q(int M, int D) {
-    // instantiated (D, Q) shapes: Q = ceil(Mpad / D) for Mpad in {64, 128}; D = 1 (plain short FIR): Q in {16, 32}
-    if (D == 1) return M <= 16 ? 16 : (M <= 32 ? 32 : 0);
-    if (D != 2 && D != 3 && D != 4 && D != 5 && D != 8 && D != 10) return 0;
-    if (M <= 64) return (64 + D - 1) / D;
-    if (M <= 128) return (128 + D - 1) / D;
+static int shape_q(int M, int D, bool rotates) {
+    // Instantiated shapes.  Each one is a handful of fully unrolled ~2500-instruction kernels (minutes of ptxas
+    // time), so the list is exactly what the reference's own graphs produce on the hot path:
+    //   (D, Q) = (5, 26): TunerBlock / DecimatorBlock with the default 128 taps and decimation 5
+    //            (examples/rtlsdr_wbfm_mono.lua), with or without the translator / discriminator;
+    //   (1, 16), (1, 32): plain FIRs with up to 16 / 32 real taps (below the overlap-save break-even).
+    // Every other decimating or translating FIR runs the overlap-save kernel (fir_fft.cu), which fuses both.
+    if (D == 1 && !rotates) return M <= 16 ? 16 : (M <= 32 ? 32 : 0);
+    if (D == 5 && M > 65 && M <= 128) return 26;
     return 0;
 }
 
 static constexpr int PT_E_LEN = 2 * 48 * PT_THREADS;   // >= LOADED of every instantiated shape
 
 PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table) {
-    int Q = shape_q(M, D);
+    int Q = shape_q(M, D, phasor_table);
     if (!Q) return nullptr;
     PolyTaps* p = new (std::nothrow) PolyTaps();
     if (!p) return nullptr;
@@ -411,12 +421,17 @@ void polyphase_release(PolyTaps* p) {
     delete p;
 }
 
-#define LRB_SHAPE(DD, QQ)                                                                                              \
+#define LRB_SHAPE_FULL(DD, QQ)                                                                                         \
     if (p->D == DD && p->Q == QQ) {                                                                                    \
         static_assert(PolyShape<DD, QQ>::ITERS <= PT_MAXIT, "step table too short");                                   \
         if (disc) return launch_shape<DD, QQ, true, true>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, prev_in, prev_out, inv_gain, s); \
         return rot ? launch_shape<DD, QQ, true, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s)    \
                    : launch_shape<DD, QQ, false, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);  \
+    }
+#define LRB_SHAPE_PLAIN(DD, QQ)                                                                                        \
+    if (p->D == DD && p->Q == QQ && !rot && !disc) {                                                                   \
+        static_assert(PolyShape<DD, QQ>::ITERS <= PT_MAXIT, "step table too short");                                   \
+        return launch_shape<DD, QQ, false, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s); \
     }
 
 static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2* hist, long long n, void* y,
@@ -436,13 +451,8 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
     std::memcpy(P.step, p->step, sizeof(P.step));
     P.g0 = g0;
     P.M = p->M;
-    LRB_SHAPE(1, 16) LRB_SHAPE(1, 32)
-    LRB_SHAPE(2, 32) LRB_SHAPE(2, 64)
-    LRB_SHAPE(3, 22) LRB_SHAPE(3, 43)
-    LRB_SHAPE(4, 16) LRB_SHAPE(4, 32)
-    LRB_SHAPE(5, 13) LRB_SHAPE(5, 26)
-    LRB_SHAPE(8, 8) LRB_SHAPE(8, 16)
-    LRB_SHAPE(10, 7) LRB_SHAPE(10, 13)
+    LRB_SHAPE_PLAIN(1, 16) LRB_SHAPE_PLAIN(1, 32)
+    LRB_SHAPE_FULL(5, 26)
     return 0;
 }
 
