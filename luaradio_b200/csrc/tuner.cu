@@ -48,7 +48,7 @@ namespace {
 #define LRB_PT_THREADS 128
 #define LRB_PT_R 8
 #define LRB_PT_CTAS 4
-#define LRB_PT_PREFETCH 14
+#define LRB_PT_PREFETCH 7
 #define LRB_PT_BATCH 7
 #endif
 constexpr int PT_THREADS = LRB_PT_THREADS;
