@@ -53,6 +53,21 @@ __device__ __forceinline__ float2 ld_cg(const float2* p) { return __ldcg(p); }
 constexpr int IIR_WARM = 512;
 constexpr int IIR_PAY = IIR_THREADS * IIR_V - IIR_WARM;   // payload samples per CTA after the first
 
+// x[b-1 .. b+8) for a real single-pole design (NBT = 2, V = 8): the 8 own samples as two 128-bit loads (32-byte aligned
+// per thread; the two instructions of a warp touch the same sectors, so L1 moves 2 KB per KB used instead of the
+// 9 KB of nine scalar loads) plus the one sample before.
+__device__ __forceinline__ void load9(const float* __restrict__ xb, float (&xv)[9]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xb + 1));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(xb + 5));
+    xv[0] = __ldg(xb);
+    xv[1] = a.x; xv[2] = a.y; xv[3] = a.z; xv[4] = a.w;
+    xv[5] = b.x; xv[6] = b.y; xv[7] = b.z; xv[8] = b.w;
+}
+__device__ __forceinline__ void load9(const float2* __restrict__ xb, float2 (&xv)[9]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) xv[i] = __ldg(xb + i);
+}
+
 // NBT: compile-time number of feed-forward taps (2 for every single-pole design of the reference; IIR_MAX_NB = generic).
 // With the generic 9-slot loops the kernel was instruction-bound (ncu: 74 % issue-active, ~70 instr per sample).
 template <typename T, bool LOCAL, int NBT>
@@ -71,6 +86,7 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
     // LOCAL: persistent CTAs, grid-stride over the tiles (`epoch` carries the tile count): 15 000 short-lived
     // 4096-sample CTAs spent most of their life in launch/drain latency
     int tile_iter = blockIdx.x;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0;   // tile/thread bases are multiples of 8 samples
     T xnext[IIR_V + NBT - 1];                         // LOCAL: next tile's inputs, fetched while this tile is scanned
     bool have_next = false;
 next_tile:
@@ -95,8 +111,16 @@ next_tile:
     } else if (base >= NBT - 1 && base + IIR_V <= n) {
         // interior thread: no bounds checks
         const T* xb = x + (base - (NBT - 1));
+        if constexpr (NBT == 2 && IIR_V == 8) {
+            if (vec_ok) load9(xb, xv);
+            else {
 #pragma unroll
-        for (int i = 0; i < IIR_V + NBT - 1; ++i) xv[i] = __ldg(xb + i);
+                for (int i = 0; i < 9; ++i) xv[i] = __ldg(xb + i);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < IIR_V + NBT - 1; ++i) xv[i] = __ldg(xb + i);
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < IIR_V + NBT - 1; ++i) {
@@ -127,8 +151,16 @@ next_tile:
             const long long nb0 = (long long)IIR_TILE + (long long)(nt - 1) * IIR_PAY - IIR_WARM + (long long)tid * IIR_V;
             if (nb0 >= NBT - 1 && nb0 + IIR_V <= n) {
                 const T* xb = x + (nb0 - (NBT - 1));
+                if constexpr (NBT == 2 && IIR_V == 8) {
+                    if (vec_ok) load9(xb, xnext);
+                    else {
 #pragma unroll
-                for (int i = 0; i < IIR_V + NBT - 1; ++i) xnext[i] = __ldg(xb + i);
+                        for (int i = 0; i < 9; ++i) xnext[i] = __ldg(xb + i);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < IIR_V + NBT - 1; ++i) xnext[i] = __ldg(xb + i);
+                }
                 have_next = true;
             }
         }

@@ -20,15 +20,20 @@
 // register window to rotate, no de-interleaving.  Thread t's samples start at element t*(R*D) and the layout is
 // padded by 2 samples every R*D, which makes the per-thread stride (R*D+2)*8 B conflict-free for 128-bit loads.
 //
-// Rotation.  x[i] e^{jw(g0+i)} = P_tile * (x[i] * E[i - B]) with E a per-handle table of the tile-relative phasors
-// (L2 resident) and P_tile the phasor of the tile origin; E is applied while staging (one complex multiply per
-// sample), P_tile commutes with the filter and is applied to the 1/D kept outputs.
+// Rotation.  x[i] e^{jw(g0+i)} = P_tile * (x[i] * E[i - B]) with E the tile-relative phasor and P_tile the phasor of
+// the tile origin.  E is applied while staging: a thread always stages the same tile-relative sample pairs, so
+// E[2u] = A0 * step[it] with A0 = E[2 tid] held in registers for the whole (persistent) kernel and step[it] a
+// per-iteration constant from the constant bank -- no table stream, no transcendental per sample.  P_tile commutes
+// with the filter and is applied to the 1/D kept outputs (not at all under the fused discriminator, which only
+// sees y[m] conj(y[m-1])).
 //
 // History of this kernel (ncu summaries in profiles/): v1 guarded loads, 1.43 ms per 256 Mi samples, 85 % of
 // stall samples on first use of a load; v2 batched loads 0.90 ms; v3 persistent + cross-tile prefetch + fused
 // discriminator 1.00 ms (0.90 + 0.13 before); a warp-specialised producer/consumer variant of v3 gained only 5 %
 // because v3 was issue-bound, not latency-bound: 60 instructions per staged sample PAIR (de-interleave index
-// arithmetic + two phasor products).  v4 (this file) stages with ~13.
+// arithmetic + two phasor products).  v4 (natural-order tile, ~13 instructions per pair, phasor table) 0.82 ms with
+// 42 % of the stall samples on the staging loads; v5 (this file: phasors by arithmetic, deeper prefetch, packed
+// 25-instruction atan2 epilogue) 0.73-0.75 ms, FP32 pipe 67 % active.
 #include "common.cuh"
 #include "blocks.h"
 
@@ -99,7 +104,7 @@ template <int D, int Q, bool ROT, bool DISC, bool EDGE>
 __global__ void __launch_bounds__(PT_THREADS, LRB_PT_CTAS)
 polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, long long n,
                       void* __restrict__ yv, long long n_out, const __grid_constant__ PolyParams P,
-                      const float2* __restrict__ E, long long t_lo, long long t_hi,
+                      long long t_lo, long long t_hi,
                       const float2* __restrict__ prev_in, float2* __restrict__ prev_out, float inv_gain) {
     using S = PolyShape<D, Q>;
     constexpr int TS = TileStride<DISC>::TS;
@@ -311,7 +316,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
 }
 
 template <int D, int Q, bool ROT, bool DISC>
-int launch_shape(PolyParams P, const float* hr_base, const float2* E, const float2* x, const float2* hist, long long n,
+int launch_shape(PolyParams P, const float* hr_base, const float2* x, const float2* hist, long long n,
                  void* y, long long first, long long n_out, const float2* prev_in, float2* prev_out, float inv_gain,
                  cudaStream_t s) {
     using S = PolyShape<D, Q>;
@@ -353,11 +358,11 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* E, const floa
     if (n_int > 0) {
         long long grid = (long long)ctx().sm_count * ctas_per_sm;
         if (grid > n_int) grid = n_int;
-        kern_i<<<(unsigned)grid, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, E, t_lo, t_hi, prev_in, prev_out, inv_gain);
+        kern_i<<<(unsigned)grid, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();
     }
     if (n_edge > 0) {
-        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, E, t_lo, t_hi, prev_in, prev_out, inv_gain);
+        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();
     }
     LRB_CHECK(cudaGetLastError());
@@ -372,7 +377,6 @@ struct PolyTaps {
     uint64_t turns_fix;
     float2 step[PT_MAXIT];       // per-staging-iteration phasor advance (see PolyParams)
     bool rotates = false;        // a translator is fused
-    float2* d_E = nullptr;       // (unused; kept so the launch signature stays put)
 };
 
 static int shape_q(int M, int D, bool rotates) {
@@ -386,8 +390,6 @@ static int shape_q(int M, int D, bool rotates) {
     if (D == 5 && M > 65 && M <= 128) return 26;
     return 0;
 }
-
-static constexpr int PT_E_LEN = 2 * 48 * PT_THREADS;   // >= LOADED of every instantiated shape
 
 PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table) {
     int Q = shape_q(M, D, phasor_table);
@@ -415,23 +417,19 @@ PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sa
     return p;
 }
 
-void polyphase_release(PolyTaps* p) {
-    if (!p) return;
-    cudaFree(p->d_E);
-    delete p;
-}
+void polyphase_release(PolyTaps* p) { delete p; }
 
 #define LRB_SHAPE_FULL(DD, QQ)                                                                                         \
     if (p->D == DD && p->Q == QQ) {                                                                                    \
         static_assert(PolyShape<DD, QQ>::ITERS <= PT_MAXIT, "step table too short");                                   \
-        if (disc) return launch_shape<DD, QQ, true, true>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, prev_in, prev_out, inv_gain, s); \
-        return rot ? launch_shape<DD, QQ, true, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s)    \
-                   : launch_shape<DD, QQ, false, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);  \
+        if (disc) return launch_shape<DD, QQ, true, true>(P, p->hr, x, hist, n, y, first, n_out, prev_in, prev_out, inv_gain, s); \
+        return rot ? launch_shape<DD, QQ, true, false>(P, p->hr, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s)    \
+                   : launch_shape<DD, QQ, false, false>(P, p->hr, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);  \
     }
 #define LRB_SHAPE_PLAIN(DD, QQ)                                                                                        \
     if (p->D == DD && p->Q == QQ && !rot && !disc) {                                                                   \
         static_assert(PolyShape<DD, QQ>::ITERS <= PT_MAXIT, "step table too short");                                   \
-        return launch_shape<DD, QQ, false, false>(P, p->hr, p->d_E, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s); \
+        return launch_shape<DD, QQ, false, false>(P, p->hr, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s); \
     }
 
 static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2* hist, long long n, void* y,
