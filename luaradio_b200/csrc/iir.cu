@@ -77,6 +77,8 @@ iir1_scan_kernel(const T* __restrict__ x, long long n, T* __restrict__ y, IirPar
                  const T* __restrict__ ystate_in, T* __restrict__ ystate_out,
                  long long first, int D, int* ticket, volatile int* flags, T* agg, T* pfx, unsigned epoch) {
     __shared__ int s_tile;
+    __shared__ int s_off;
+    __shared__ long long s_q;
     __shared__ T s_warp[IIR_THREADS / 32];
     __shared__ T s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -99,6 +101,13 @@ next_tile:
         __syncthreads();
         tile = s_tile;
         span0 = pay0 = (long long)tile * IIR_TILE;
+    }
+    if (D > 1 && tid == 0) {
+        // decimation phase of this span, once per tile: floor-div/mod of (span0 - first) by D
+        long long d0 = span0 - first, qq = d0 / D, rr = d0 - qq * D;
+        if (rr < 0) { rr += D; qq -= 1; }
+        s_off = (int)rr;
+        s_q = qq;
     }
     const long long base = span0 + (long long)tid * IIR_V;
     const int nh = P.nb - 1;
@@ -177,6 +186,8 @@ next_tile:
     T prevB = shfl_up_t(B, 1);                      // inclusive value of lane-1 (zero-state from warp start)
     if (lane == 0) prevB = zero_of(T());
     __syncthreads();
+    const int dec_off = (D > 1) ? s_off : 0;        // read here: thread 0 rewrites them at the top of its next pass
+    const long long dec_q = (D > 1) ? s_q : 0;
     T carryW = zero_of(T());                        // value at the end of warp-1, zero-state from tile start
     for (int w = 0; w < warp; ++w) carryW = fmas(P.cp[5], carryW, s_warp[w]);
     float f_lane = 1.f;                             // c^(V*lane)
@@ -248,39 +259,47 @@ next_tile:
     for (int k = 0; k < IIR_LOGW; ++k) if (warp & (1 << k)) f_thread *= P.cp[5 + k];
     const T carry_t = fmas(f_thread, carry_in, excl);
 
-    // ---- outputs y[i] = yl[i] + c^(i+1) * carry_t.  Fused decimation keeps sample idx when (idx - first) % D == 0;
-    // the residue/quotient are tracked incrementally from one 32-bit division per thread (a 64-bit division per
-    // sample made the first version instruction-bound: 140 instructions per sample in ncu).
-    int res = 0;
-    long long jout = 0;
-    if (D > 1) {
-        const long long d0 = base - first;
-        if (d0 >= 0) {
-            const unsigned q = (unsigned)d0 / (unsigned)D;
-            res = (int)((unsigned)d0 - q * (unsigned)D);
-            jout = (long long)q + (res ? 1 : 0);          // index of the next kept sample
-            res = res ? res - D : 0;                      // res <= 0: samples until the next kept one (negated)
+    // ---- outputs y[i] = yl[i] + c^(i+1) * carry_t, stored with tile-relative 32-bit bookkeeping.  (The first
+    // versions did a 64-bit division, then several 64-bit compares, per sample: ncu showed 68 % of the executed
+    // instructions after the last barrier.)  rel = index relative to span0; [lo, hi) is what this CTA stores.
+    const int rel0 = tid * IIR_V;
+    const int lo = (int)(pay0 - span0);
+    const long long remain = n - span0;
+    const int hi = remain < (long long)IIR_TILE ? (int)remain : IIR_TILE;
+    T vals[IIR_V];
+    {
+        float cpow = P.c;
+#pragma unroll
+        for (int i = 0; i < IIR_V; ++i) { vals[i] = fmas(cpow, carry_t, yl[i]); cpow *= P.c; }
+    }
+    if (D == 1) {
+        T* yo = y + span0 + rel0;
+        if (rel0 >= lo && rel0 + IIR_V <= hi) {
+#pragma unroll
+            for (int i = 0; i < IIR_V; ++i) yo[i] = vals[i];
         } else {
-            res = (int)d0;                                // before the first kept sample
+#pragma unroll
+            for (int i = 0; i < IIR_V; ++i) if (rel0 + i >= lo && rel0 + i < hi) yo[i] = vals[i];
+        }
+    } else {
+        // kept samples: (span0 + rel - first) % D == 0  <=>  (rel + s_off) % D == 0, output index s_q + (rel + s_off) / D
+        const unsigned e = (unsigned)(rel0 + dec_off);
+        const unsigned q = e / (unsigned)D, r = e - q * (unsigned)D;
+        int knext = r ? (int)((unsigned)D - r) : 0;               // first kept sample of this thread (offset in 0..)
+        T* yo = y + (dec_q + (long long)q + (r ? 1 : 0));
+#pragma unroll
+        for (int i = 0; i < IIR_V; ++i) {
+            if (i == knext) {
+                if (rel0 + i >= lo && rel0 + i < hi) *yo = vals[i];
+                ++yo;
+                knext += D;
+            }
         }
     }
-    float cpow = P.c;
+    if (remain <= (long long)IIR_TILE && hi - 1 >= rel0 && hi - 1 < rel0 + IIR_V) {
+        // the stream's last sample lives in this thread: carried output state
 #pragma unroll
-    for (int i = 0; i < IIR_V; ++i) {
-        long long idx = base + i;
-        T v = fmas(cpow, carry_t, yl[i]);
-        cpow *= P.c;
-        if (idx < n && idx >= pay0) {
-            if (D == 1) {
-                y[idx] = v;
-            } else if (res == 0) {
-                y[jout] = v;
-            }
-            if (idx == n - 1) *ystate_out = v;
-        }
-        if (D > 1) {
-            if (res == 0) { res = 1 - D; ++jout; } else { ++res; }
-        }
+        for (int i = 0; i < IIR_V; ++i) if (rel0 + i == hi - 1) *ystate_out = vals[i];
     }
     // ---- carried input history for the next call: last nb-1 inputs of [xhist_in | x]
     if (tile == 0 && tid < nh) {
