@@ -33,6 +33,23 @@ bool cuda_ok(cudaError_t e, const char* what) {
     return false;
 }
 
+cudaStream_t side_fork(cudaStream_t s) {
+    Ctx& c = g_ctx;
+    if (!c.side) {
+        if (cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking) != cudaSuccess) { c.side = nullptr; return s; }
+        cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c.ev_join, cudaEventDisableTiming);
+    }
+    if (cudaEventRecord(c.ev_fork, s) != cudaSuccess || cudaStreamWaitEvent(c.side, c.ev_fork, 0) != cudaSuccess) return s;
+    return c.side;
+}
+
+void side_join(cudaStream_t s, cudaStream_t side) {
+    if (side == s) return;
+    cudaEventRecord(g_ctx.ev_join, side);
+    cudaStreamWaitEvent(s, g_ctx.ev_join, 0);
+}
+
 static int ensure_init() {
     if (g_ctx.device >= 0) return 0;
     return lrb200_init(0);

@@ -15,6 +15,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::atomic<uint64_t> launches{0};
+    // side stream for the few-CTA edge kernels, so they overlap the interior kernel instead of trailing it
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 Ctx& ctx();
 void set_error(const char* fmt, ...);
@@ -35,6 +38,11 @@ inline uint64_t turns_to_fix(double turns) {
     if (f >= 18446744073709551616.0L) return 0;
     return (uint64_t)f;
 }
+
+// fork: returns a stream that has waited for everything enqueued on `s` so far (or `s` itself if unavailable);
+// join: makes `s` wait for the side stream.  Used as  side = side_fork(s); edge<<<..., side>>>; main<<<..., s>>>; side_join(s).
+cudaStream_t side_fork(cudaStream_t s);
+void side_join(cudaStream_t s, cudaStream_t side);
 
 inline void count_launch(int n = 1) { ctx().launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 

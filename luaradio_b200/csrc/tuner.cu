@@ -355,16 +355,19 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
         if (t_lo > t_hi) t_lo = t_hi;
     }
     const long long n_int = t_hi - t_lo, n_edge = tiles - n_int;
+    // the edge tiles (first / last few) go to the side stream so that they overlap the interior kernel
+    cudaStream_t side = (n_int > 0 && n_edge > 0) ? side_fork(s) : s;
+    if (n_edge > 0) {
+        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, side>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
+        count_launch();
+    }
     if (n_int > 0) {
         long long grid = (long long)ctx().sm_count * ctas_per_sm;
         if (grid > n_int) grid = n_int;
         kern_i<<<(unsigned)grid, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();
     }
-    if (n_edge > 0) {
-        kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
-        count_launch();
-    }
+    side_join(s, side);
     LRB_CHECK(cudaGetLastError());
     return 1;
 }
