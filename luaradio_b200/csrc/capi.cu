@@ -160,15 +160,17 @@ int FirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_
     decim_plan(consumed, (unsigned)D, n, &first, &no);
     *n_out = (size_t)no;
     if (n == 0) return 0;
-    int rc = fast_run(dx, n, dy, first, no, s);
-    if (rc < 0) return -1;
-    if (rc == 0) {
-        if (launch_fir_generic(kind, dx, d_hist[cur], d_taps, M, D, first, no, dy, s) != 0) return -1;
-    }
+    // the history for the next call depends only on x and the old history: side stream, concurrent with the filter
+    cudaStream_t side = s;
     if (M > 1) {
-        if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, (int)in_size, s) != 0) return -1;
-        cur ^= 1;
+        side = side_fork(s);
+        if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, (int)in_size, side) != 0) return -1;
     }
+    int rc = fast_run(dx, n, dy, first, no, s);
+    if (rc == 0) rc = launch_fir_generic(kind, dx, d_hist[cur], d_taps, M, D, first, no, dy, s) == 0 ? 1 : -1;
+    side_join(s, side);
+    if (rc < 0) return -1;
+    if (M > 1) cur ^= 1;
     consumed += n;
     return 0;
 }

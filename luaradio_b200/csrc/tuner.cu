@@ -518,15 +518,20 @@ struct TunerBlock : Block {
         long long no = ((long long)n > first) ? (((long long)n - first + D - 1) / D) : 0;
         *n_out = (size_t)no;
         if (n == 0) return 0;
+        // the history for the next call depends only on x and the old history: update it on the side stream,
+        // concurrently with the filter kernels
+        cudaStream_t side = s;
+        if (M > 1) {
+            side = side_fork(s);
+            if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, 8, side) != 0) return -1;
+        }
         int rc = launch_polyphase_any(pt, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, dy, first, no, true,
                                       disc, consumed, (const float2*)d_prev[pcur], (float2*)d_prev[pcur ^ 1],
                                       disc ? 1.0f / gain : 0.f, s);
+        side_join(s, side);
         if (rc <= 0) { if (rc == 0) set_error("tuner: unsupported shape"); return -1; }
         if (disc && no > 0) pcur ^= 1;
-        if (M > 1) {
-            if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, 8, s) != 0) return -1;
-            cur ^= 1;
-        }
+        if (M > 1) cur ^= 1;
         consumed += n;
         return 0;
     }
