@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include <vector>
 #include <string>
+#include <utility>
 
 namespace lrb {
 
@@ -19,7 +20,11 @@ struct Block {
     virtual size_t max_output(size_t n) const { return n; }
     // device pointers in/out, asynchronous on s; consumes n, produces *n_out, advances the carried state
     virtual int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) = 0;
-    virtual int reset() { consumed = 0; return 0; }
+    // reset = host-side bookkeeping + zeroing the device state buffers; a graph zeroes every stage's buffers with ONE
+    // kernel (a 256 Mi-sample chain step is ~1 ms: a dozen cudaMemsetAsync nodes per step were 1.5 % of it)
+    virtual void reset_host() { consumed = 0; }
+    virtual void state_buffers(std::vector<std::pair<void*, size_t>>& segs) { (void)segs; }
+    int reset();
     virtual int seek(uint64_t idx) { consumed = idx; return 0; }
     // number of outputs this block has produced once `idx` inputs are consumed (for graph seek)
     virtual uint64_t outputs_before(uint64_t idx) const { return idx; }
@@ -51,7 +56,8 @@ struct FirBlock : Block {
     int init() override;
     size_t max_output(size_t n) const override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
-    int reset() override;
+    void reset_host() override;
+    void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
     // fast paths (fir_fft.cu): fast_run returns 1 if it handled the call, 0 to fall back, <0 on error
     int fast_init();
@@ -74,7 +80,8 @@ struct DiscrimBlock : Block {
     DiscrimBlock(float gain, bool dev);
     ~DiscrimBlock() override;
     int init() override;
-    int reset() override;
+    void reset_host() override;
+    void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
 };
 
@@ -100,7 +107,8 @@ struct IirBlock : Block {
     ~IirBlock() override;
     int init() override;
     size_t max_output(size_t n) const override;
-    int reset() override;
+    void reset_host() override;
+    void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
 };
@@ -117,7 +125,8 @@ struct IirGeneralBlock : Block {
     IirGeneralBlock(bool cplx, const float* b, unsigned nb, const float* a, unsigned na, bool dev);
     ~IirGeneralBlock() override;
     int init() override;
-    int reset() override;
+    void reset_host() override;
+    void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
 };
 

@@ -75,6 +75,14 @@ int Block::reserve(void** p, size_t* cap, size_t bytes) {
     return 0;
 }
 
+int Block::reset() {
+    reset_host();
+    std::vector<std::pair<void*, size_t>> segs;
+    state_buffers(segs);
+    for (auto& sg : segs) LRB_CHECK(cudaMemsetAsync(sg.first, 0, sg.second, ctx().stream));
+    return 0;
+}
+
 int Block::execute(const void* x, size_t n, void* y, size_t* n_out) {
     cudaStream_t s = ctx().stream;
     size_t produced = 0;
@@ -146,13 +154,11 @@ FirBlock::~FirBlock() {
 
 size_t FirBlock::max_output(size_t n) const { return D == 1 ? n : n / D + 1; }
 
-int FirBlock::reset() {
-    consumed = 0;
-    cur = 0;
-    size_t hb = (size_t)(M > 1 ? M - 1 : 1) * in_size;
-    LRB_CHECK(cudaMemsetAsync(d_hist[0], 0, hb, ctx().stream));
-    LRB_CHECK(cudaMemsetAsync(d_hist[1], 0, hb, ctx().stream));
-    return 0;
+void FirBlock::reset_host() { consumed = 0; cur = 0; }
+void FirBlock::state_buffers(std::vector<std::pair<void*, size_t>>& segs) {
+    const size_t hb = (size_t)(M > 1 ? M - 1 : 1) * in_size;
+    segs.push_back({d_hist[0], hb});
+    segs.push_back({d_hist[1], hb});
 }
 
 int FirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
@@ -209,11 +215,8 @@ int DiscrimBlock::init() {
     return 0;
 }
 DiscrimBlock::~DiscrimBlock() { cudaFree(d_prev); }
-int DiscrimBlock::reset() {
-    consumed = 0;
-    LRB_CHECK(cudaMemsetAsync(d_prev, 0, sizeof(float2), ctx().stream));
-    return 0;
-}
+void DiscrimBlock::reset_host() { consumed = 0; }
+void DiscrimBlock::state_buffers(std::vector<std::pair<void*, size_t>>& segs) { segs.push_back({d_prev, sizeof(float2)}); }
 int DiscrimBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
     *n_out = n;
     if (n == 0) return 0;
@@ -270,15 +273,10 @@ IirBlock::~IirBlock() {
     iir_work_free(&work);
 }
 size_t IirBlock::max_output(size_t n) const { return D == 1 ? n : n / D + 1; }
-int IirBlock::reset() {
-    consumed = 0;
-    cur = 0;
-    size_t hb = (size_t)(nb > 1 ? nb - 1 : 1) * in_size;
-    for (int i = 0; i < 2; ++i) {
-        LRB_CHECK(cudaMemsetAsync(d_xhist[i], 0, hb, ctx().stream));
-        LRB_CHECK(cudaMemsetAsync(d_ystate[i], 0, in_size, ctx().stream));
-    }
-    return 0;
+void IirBlock::reset_host() { consumed = 0; cur = 0; }
+void IirBlock::state_buffers(std::vector<std::pair<void*, size_t>>& segs) {
+    const size_t hb = (size_t)(nb > 1 ? nb - 1 : 1) * in_size;
+    for (int i = 0; i < 2; ++i) { segs.push_back({d_xhist[i], hb}); segs.push_back({d_ystate[i], in_size}); }
 }
 int IirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
     long long first_total, no_total;
@@ -341,14 +339,9 @@ int IirGeneralBlock::init() {
 IirGeneralBlock::~IirGeneralBlock() {
     for (int i = 0; i < 2; ++i) { cudaFree(d_xhist[i]); cudaFree(d_yhist[i]); }
 }
-int IirGeneralBlock::reset() {
-    consumed = 0;
-    cur = 0;
-    for (int i = 0; i < 2; ++i) {
-        LRB_CHECK(cudaMemsetAsync(d_xhist[i], 0, 10 * in_size, ctx().stream));
-        LRB_CHECK(cudaMemsetAsync(d_yhist[i], 0, 10 * in_size, ctx().stream));
-    }
-    return 0;
+void IirGeneralBlock::reset_host() { consumed = 0; cur = 0; }
+void IirGeneralBlock::state_buffers(std::vector<std::pair<void*, size_t>>& segs) {
+    for (int i = 0; i < 2; ++i) { segs.push_back({d_xhist[i], 10 * in_size}); segs.push_back({d_yhist[i], 10 * in_size}); }
 }
 int IirGeneralBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
     *n_out = n;

@@ -64,6 +64,8 @@ int launch_downsample(const void* x, void* y, long long first, long long n_out, 
 int launch_cmag(const float2* x, float* y, long long n, cudaStream_t s);
 int launch_c2r(const float2* x, float* y, long long n, cudaStream_t s);
 int launch_copy_last(const void* x, long long n, void* dst, int elem_size, cudaStream_t s);
+// zero up to 32 small device buffers with one launch (graph reset)
+int launch_zero_segments(void* const* ptrs, const size_t* bytes, int count, cudaStream_t s);
 
 // ---- iir.cu -----------------------------------------------------------------------------------
 // y[n] = sum_{j<nb} b[j] x[n-j] + c*y[n-1]   (c = -a1/a0, b already divided by a0)

@@ -84,7 +84,27 @@ __global__ void copy_last_kernel(const char* __restrict__ x, long long n, char* 
     if (t < elem_size) dst[t] = x[(n - 1) * elem_size + t];
 }
 
+struct ZeroSegs { void* p[32]; unsigned long long bytes[32]; int count; };
+__global__ void zero_segments_kernel(ZeroSegs z) {
+    for (int k = blockIdx.x; k < z.count; k += gridDim.x) {
+        char* p = (char*)z.p[k];
+        for (unsigned long long i = threadIdx.x; i < z.bytes[k]; i += blockDim.x) p[i] = 0;
+    }
+}
+
 }  // namespace
+
+int launch_zero_segments(void* const* ptrs, const size_t* bytes, int count, cudaStream_t s) {
+    for (int done = 0; done < count; done += 32) {
+        ZeroSegs z;
+        z.count = count - done < 32 ? count - done : 32;
+        for (int k = 0; k < z.count; ++k) { z.p[k] = ptrs[done + k]; z.bytes[k] = bytes[done + k]; }
+        zero_segments_kernel<<<z.count, 256, 0, s>>>(z);
+        count_launch();
+    }
+    LRB_CHECK(cudaGetLastError());
+    return 0;
+}
 
 int launch_fir_generic(FirKind kind, const void* x, const void* hist, const void* taps, int M, int D,
                        long long first, long long n_out, void* y, cudaStream_t s) {

@@ -221,9 +221,14 @@ struct Graph {
     }
 
     int reset() {
-        for (Block* b : blocks) if (b->reset() != 0) return -1;
-        for (Block* b : fused) if (b->reset() != 0) return -1;
-        return 0;
+        std::vector<std::pair<void*, size_t>> segs;
+        for (Block* b : blocks) { b->reset_host(); b->state_buffers(segs); }
+        for (Block* b : fused) { b->reset_host(); b->state_buffers(segs); }
+        if (segs.empty()) return 0;
+        std::vector<void*> ptrs;
+        std::vector<size_t> bytes;
+        for (auto& sg : segs) { ptrs.push_back(sg.first); bytes.push_back(sg.second); }
+        return launch_zero_segments(ptrs.data(), bytes.data(), (int)ptrs.size(), ctx().stream);
     }
 
     int seek(uint64_t idx) {

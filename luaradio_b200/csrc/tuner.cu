@@ -502,15 +502,10 @@ struct TunerBlock : Block {
     }
     size_t max_output(size_t n) const override { return n / D + 1; }
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
-    int reset() override {
-        consumed = 0;
-        cur = pcur = 0;
-        size_t hb = (size_t)(M > 1 ? M - 1 : 1) * 8;
-        for (int i = 0; i < 2; ++i) {
-            LRB_CHECK(cudaMemsetAsync(d_hist[i], 0, hb, ctx().stream));
-            LRB_CHECK(cudaMemsetAsync(d_prev[i], 0, 8, ctx().stream));
-        }
-        return 0;
+    void reset_host() override { consumed = 0; cur = pcur = 0; }
+    void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override {
+        const size_t hb = (size_t)(M > 1 ? M - 1 : 1) * 8;
+        for (int i = 0; i < 2; ++i) { segs.push_back({d_hist[i], hb}); segs.push_back({d_prev[i], 8}); }
     }
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override {
         uint64_t r = consumed % (uint64_t)D;
