@@ -119,12 +119,14 @@ def chain_taps():
     return t1, t2, b, a
 
 
-def build_chain_graph(lib, _lib):
-    """The rtlsdr_wbfm_mono.lua chain as C-ABI blocks appended to a GPU flow graph (what CompositeBlock.run builds)."""
+def build_chain_graph(lib, _lib, iq_format=None):
+    """The rtlsdr_wbfm_mono.lua chain as C-ABI blocks appended to a GPU flow graph (what CompositeBlock.run builds).
+    `iq_format`: prepend the source-boundary sample-format converter (raw file/dongle bytes in)."""
     t1, t2, b, a = chain_taps()
     D = _lib.LRB200_DEVICE
     g = _lib.check_handle(lib.lrb200_graph_create(), "graph")
-    blocks = [
+    blocks = [lib.lrb200_iqconv_create(iq_format.encode(), D)] if iq_format else []
+    blocks += [
         lib.lrb200_rotator_create(TUNE_OFFSET / RATE, D),
         lib.lrb200_fir_create_crcf(t1.ctypes.data, 128, 1, D),
         lib.lrb200_downsample_create(5, 8, D),
@@ -247,6 +249,39 @@ def run_b200(args):
     e2e_value = world * n / float(te.item()) / 1e6
     n_out_step = int(n_out.value)
 
+    # ---- the same end-to-end call fed the RTL-SDR's native u8 I/Q bytes (2 B/sample over PCIe, converted on the
+    # device by the graph's first stage) -- extra information, N == 1 only; the headline e2e stays the f32 boundary
+    e2e_u8 = None
+    if world == 1:
+        g8 = build_chain_graph(lib, _lib, "u8")
+        h8 = lib.lrb200_host_alloc(n * 2)
+        assert h8, _lib.last_error()
+        xr = torch.view_as_real(x[HALO:HALO + n])
+        CH = 1 << 24
+        for o in range(0, n, CH):      # quantise the synthetic samples to u8 on the device, park them in pinned host memory
+            q = (xr[o:o + CH] * 127.5 + 127.5).round_().clamp_(0, 255).to(torch.uint8).contiguous()
+            _lib.check(lib.lrb200_memcpy_d2h(ctypes.c_void_p(h8 + o * 2), ctypes.c_void_p(q.data_ptr()), q.numel()), "d2h")
+            _lib.check(lib.lrb200_sync(), "sync")
+            torch.cuda.synchronize()
+        del q, xr
+
+        def e2e8_step():
+            _lib.check(lib.lrb200_graph_reset(g8), "reset")
+            _lib.check(lib.lrb200_graph_execute(g8, h8, n, hout, ctypes.byref(n_out)), "graph_execute(host,u8)")
+
+        e2e8_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e8_step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        e2e_u8 = {"value": round(n / ((t1 - t0) / e2e_steps) / 1e6, 1), "unit": "Msamples/s", "h2d_bytes_per_step": n * 2,
+                  "d2h_bytes_per_step": int(n_out.value) * 4, "graph": lib.lrb200_graph_describe(g8).decode(),
+                  "note": "input = raw u8 I/Q bytes (IQFileSource/RtlSdrSource format), converted by the graph's first stage"}
+        lib.lrb200_host_free(h8)
+        lib.lrb200_graph_destroy(g8)
+
     result = None
     if rank == 0:
         peak, peak_src = peaks()
@@ -282,6 +317,8 @@ def run_b200(args):
                     "d2h_bytes_per_step": n_out_step * 4, "api": "lrb200_graph_execute (host pointers)", "steps": e2e_steps},
             "clocks": clocks,
         }
+        if e2e_u8:
+            result["e2e_u8"] = e2e_u8
     lib.lrb200_host_free(hin)
     lib.lrb200_host_free(hout)
     lib.lrb200_graph_destroy(g)

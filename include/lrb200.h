@@ -156,6 +156,14 @@ lrb200_iir_t* lrb200_iir_create_crcf(const float32_t* b, unsigned nb, const floa
 lrb200_block_t* lrb200_cmag_create(unsigned flags);
 lrb200_block_t* lrb200_c2r_create(unsigned flags);
 
+/* ---- IQFileSource sample formats (the source boundary) ------------------------------
+ * Replaces the byte-swap + (value - offset) / scale loops of radio/blocks/sources/iqfile.lua:96-108 with the format
+ * table of radio/utilities/format_utils.lua:82-97: u8 s8 u16le u16be s16le s16be u32le u32be s32le s32be f32le f32be
+ * f64le f64be.  Input: interleaved I/Q in the file's own byte order (2 * sizeof(component) bytes per sample);
+ * output: ComplexFloat32.  As the first stage of a graph it makes the host->device copy carry the file bytes
+ * (2 B/sample for u8 instead of 8).  Unknown format -> NULL with "Unsupported format". */
+lrb200_block_t* lrb200_iqconv_create(const char* format, unsigned flags);
+
 /* ---- GPU flow graph: connected GPU blocks on one stream with device-resident buffers ----------
  * Replaces, for a connected run of GPU blocks, the fork-per-block + socketpair plumbing of
  * radio/core/composite.lua:568-636 and radio/core/pipe.lua:53-88,495-615: the chain

@@ -58,6 +58,7 @@ _PROTOS = {
     "lrb200_iir_create_crcf": (c_void_p, [c_void_p, c_uint, c_void_p, c_uint, c_uint]),
     "lrb200_cmag_create": (c_void_p, [c_uint]),
     "lrb200_c2r_create": (c_void_p, [c_uint]),
+    "lrb200_iqconv_create": (c_void_p, [c_char_p, c_uint]),
     "lrb200_graph_create": (c_void_p, []),
     "lrb200_graph_append": (c_int, [c_void_p, c_void_p]),
     "lrb200_graph_commit": (c_int, [c_void_p, c_int]),

@@ -47,6 +47,74 @@ class ArraySource(Block):
         return v
 
 
+class IQFileSource(Block):
+    """radio/blocks/sources/iqfile.lua:27-116: interleaved I/Q in one of 14 sample formats -> ComplexFloat32.
+    `file` is a path, an open binary file, or a bytes-like object.  The format conversion (byte swap, offset,
+    scale; iqfile.lua:96-108) runs on the GPU: process() converts one chunk through the C ABI; inside a GPU flow
+    graph the converter becomes the graph's first stage and the RAW bytes cross PCIe (2 B/sample for "u8")."""
+    name = "IQFileSource"
+    FORMATS = {"u8": 1, "s8": 1, "u16le": 2, "u16be": 2, "s16le": 2, "s16be": 2, "u32le": 4, "u32be": 4,
+               "s32le": 4, "s32be": 4, "f32le": 4, "f32be": 4, "f64le": 8, "f64be": 8}
+
+    def instantiate(self, file, format, rate, repeat_on_eof=False, chunk=8192):
+        assert file is not None, "Missing argument #1 (file)"
+        assert format is not None, "Missing argument #2 (format)"
+        assert format in self.FORMATS, 'Unsupported format ("%s")' % format
+        assert rate is not None, "Missing argument #3 (rate)"
+        self.file, self.format, self.rate, self.repeat_on_eof = file, format, float(rate), repeat_on_eof
+        self.sample_bytes = 2 * self.FORMATS[format]
+        self.chunk_size = int(chunk)          # samples per read; the reference uses 8192 (iqfile.lua:52)
+        self._handle = None
+        self.add_type_signature([], [Output("out", ComplexFloat32)])
+
+    def get_rate(self):
+        return self.rate
+
+    def initialize(self):
+        if isinstance(self.file, (bytes, bytearray, memoryview, np.ndarray)):
+            self._buf = np.frombuffer(bytes(self.file) if not isinstance(self.file, np.ndarray) else self.file.tobytes(), np.uint8)
+        elif isinstance(self.file, str):
+            self._buf = np.fromfile(self.file, np.uint8)
+        else:
+            self._buf = np.frombuffer(self.file.read(), np.uint8)
+        self._pos = 0
+        self.out = ComplexFloat32.vector()
+
+    def read_raw(self):
+        """Next chunk of raw file bytes (whole samples), or None at EOF."""
+        nbytes = self.chunk_size * self.sample_bytes
+        if self._pos >= len(self._buf) - self.sample_bytes + 1:
+            if not self.repeat_on_eof or len(self._buf) < self.sample_bytes:
+                return None
+            self._pos = 0
+        raw = self._buf[self._pos:self._pos + nbytes]
+        raw = raw[:len(raw) // self.sample_bytes * self.sample_bytes]
+        self._pos += len(raw)
+        return np.ascontiguousarray(raw)
+
+    def make_device_handle(self):
+        lib = _lib.require_device()
+        return _lib.check_handle(lib.lrb200_iqconv_create(self.format.encode(), _lib.LRB200_DEVICE), "lrb200 iqconv object")
+
+    def process(self):
+        raw = self.read_raw()
+        if raw is None:
+            return None
+        lib = _lib.require_device()
+        if self._handle is None:
+            self._handle = _lib.check_handle(lib.lrb200_iqconv_create(self.format.encode(), _lib.LRB200_HOST), "lrb200 iqconv object")
+        n = len(raw) // self.sample_bytes
+        out = self.out.resize(n)
+        n_out = ctypes.c_size_t(0)
+        _lib.check(lib.lrb200_block_execute(self._handle, raw.ctypes.data, n, out.ctypes_ptr(), ctypes.byref(n_out)), "iqconv")
+        return out.resize(n_out.value)
+
+    def cleanup(self):
+        if self._handle:
+            _lib.load().lrb200_block_destroy(self._handle)
+            self._handle = None
+
+
 class ArraySink(Block):
     name = "ArraySink"
 
@@ -241,7 +309,10 @@ class CompositeBlock(Block):
         lib = _lib.require_device()
         source, sink, blocks = chain[0], chain[-1], chain[1:-1]
         g = _lib.check_handle(lib.lrb200_graph_create(), "lrb200 graph")
+        raw_source = isinstance(source, IQFileSource)
         try:
+            if raw_source:      # the file's sample format is converted on the device, as the first graph stage
+                _lib.check(lib.lrb200_graph_append(g, source.make_device_handle()), "graph_append(iqconv)")
             for b in blocks:
                 h = b.make_device_handle()
                 _lib.check(lib.lrb200_graph_append(g, h), "graph_append(%s)" % b.name)
@@ -250,12 +321,19 @@ class CompositeBlock(Block):
             out_type = blocks[-1].get_output_type()
             out = out_type.vector()
             while True:
-                x = source.process()
-                if x is None:
-                    break
-                out.resize(lib.lrb200_graph_max_output(g, x.length))
+                if raw_source:
+                    raw = source.read_raw()
+                    if raw is None:
+                        break
+                    n_in, in_ptr = len(raw) // source.sample_bytes, raw.ctypes.data
+                else:
+                    x = source.process()
+                    if x is None:
+                        break
+                    n_in, in_ptr = x.length, x.ctypes_ptr()
+                out.resize(lib.lrb200_graph_max_output(g, n_in))
                 n_out = ctypes.c_size_t(0)
-                _lib.check(lib.lrb200_graph_execute(g, x.ctypes_ptr(), x.length, out.ctypes_ptr(), ctypes.byref(n_out)), "graph_execute")
+                _lib.check(lib.lrb200_graph_execute(g, in_ptr, n_in, out.ctypes_ptr(), ctypes.byref(n_out)), "graph_execute")
                 out.resize(n_out.value)
                 sink.process(out)
         finally:

@@ -150,6 +150,8 @@ int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist
                           long long first, long long n_out, bool rotate, uint64_t turns_fix, uint64_t g0,
                           cudaStream_t s);
 // tuner.cu: fused FrequencyTranslator -> FIR(crcf) -> Downsampler; returns nullptr (with the error set) on failure
+// iqconv.cu: IQFileSource sample format -> ComplexFloat32 (nullptr + error for an unknown format)
+Block* make_iqconv(const char* format, bool dev);
 // disc_gain != 0 additionally fuses a FrequencyDiscriminator(gain) behind it (float output)
 Block* make_tuner(double turns_per_sample, const float* taps, int ntaps, int decim, float disc_gain);
 }  // namespace lrb

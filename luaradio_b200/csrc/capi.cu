@@ -572,6 +572,13 @@ lrb200_block_t* lrb200_c2r_create(unsigned flags) {
     return wrap(new (std::nothrow) C2fBlock(1, (flags & LRB200_DEVICE) != 0));
 }
 
+lrb200_block_t* lrb200_iqconv_create(const char* format, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    Block* b = make_iqconv(format, (flags & LRB200_DEVICE) != 0);
+    if (!b) return nullptr;
+    return wrap(b);
+}
+
 // ---- synthetic sources -------------------------------------------------------------------------
 int lrb200_synth_white_iq(complex_float32_t* dst, uint64_t n0, size_t n, uint32_t seed) {
     if (ensure_init() != 0) return -1;

@@ -542,3 +542,28 @@ def synth_fm_iq(n0, n, seed=1, rate=1102500.0, carrier=250e3, deviation=75e3, am
     a, b = _u01_pair(np.arange(n0, n0 + n, dtype=np.uint64), seed)
     x = amp * np.exp(1j * ph) + noise * (a.astype(np.float64) + 1j * b.astype(np.float64))
     return x.astype(C64)
+
+
+# ----------------------------------------------------------------------------------------------
+# the source boundary.  IQFileSource sample formats -> ComplexFloat32
+# ----------------------------------------------------------------------------------------------
+
+IQ_FORMATS = {
+    # radio/utilities/format_utils.lua:82-97: numpy dtype (file byte order), offset, scale
+    "u8": ("u1", 127.5, 127.5), "s8": ("i1", 0.0, 127.5),
+    "u16le": ("<u2", 32767.5, 32767.5), "u16be": (">u2", 32767.5, 32767.5),
+    "s16le": ("<i2", 0.0, 32767.5), "s16be": (">i2", 0.0, 32767.5),
+    "u32le": ("<u4", 2147483647.5, 2147483647.5), "u32be": (">u4", 2147483647.5, 2147483647.5),
+    "s32le": ("<i4", 0.0, 2147483647.5), "s32be": (">i4", 0.0, 2147483647.5),
+    "f32le": ("<f4", 0.0, 1.0), "f32be": (">f4", 0.0, 1.0),
+    "f64le": ("<f8", 0.0, 1.0), "f64be": (">f8", 0.0, 1.0),
+}
+
+
+def iq_file_convert(raw, fmt):
+    """radio/blocks/sources/iqfile.lua:82-116: interleaved I/Q of `fmt` -> complex64:
+    byte swap if needed (:96-101), then (value - offset) / scale in double, stored as float32 (:105-108)."""
+    dt, offset, scale = IQ_FORMATS[fmt]
+    v = np.frombuffer(np.asarray(raw, dtype=np.uint8).tobytes(), dtype=np.dtype(dt)).astype(np.float64)
+    y = ((v - offset) / scale).astype(F32)
+    return (y[0::2] + 1j * y[1::2]).astype(C64)

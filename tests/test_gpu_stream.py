@@ -304,3 +304,19 @@ def test_general_iir_long_stream(cplx):
             blk = mk(radio.IIRFilterBlock, [Float32.vector_from_array(b), Float32.vector_from_array(a)], t)
             close(stream(blk, x, cuts), ref)
             blk.cleanup()
+
+
+def test_wbfm_chain_from_u8_iq_file():
+    """RTL-SDR style u8 IQ 'file' -> fused WBFM chain in one flow graph (raw bytes over PCIe) == oracle on the
+    oracle-converted samples."""
+    n = 500000
+    x = O.synth_fm_iq(0, n)
+    u8 = np.clip(np.round(np.stack([x.real, x.imag], 1).reshape(-1) * 127.5 + 127.5), 0, 255).astype(np.uint8)
+    src, snk = radio.IQFileSource(u8.tobytes(), "u8", 1102500.0, chunk=200001), radio.ArraySink()
+    top = radio.CompositeBlock()
+    top.connect(src, radio.TunerBlock(-250e3, 200e3, 5), radio.FrequencyDiscriminatorBlock(1.25),
+                radio.LowpassFilterBlock(128, 15e3), radio.FMDeemphasisFilterBlock(75e-6), radio.DownsamplerBlock(5), snk)
+    top.run(False)
+    ref = O.wbfm_mono_chain().process(O.iq_file_convert(u8, "u8"))
+    close(snk.result(), ref)
+    assert top.describe_gpu_graph().startswith("iqconv(u8) | tuner+discrim")

@@ -104,3 +104,11 @@ def test_oracle_chunking_invariance():
     got = np.concatenate(outs)
     assert got.shape == whole.shape
     assert np.max(np.abs(got - whole)) < 1e-6
+
+
+def test_oracle_iq_file_formats():
+    """tests/blocks/sources/iqfile_spec.py: all 14 sample formats of IQFileSource at 1e-6."""
+    z = np.load(GOLDEN_DIR + "/iqfile_spec_raw.npz")
+    for i, fmt in enumerate(z["formats"]):
+        ok, msg = epsilon_ok(O.iq_file_convert(z["v%d_raw" % i], str(fmt)), z["v%d_out" % i], 1e-6)
+        assert ok, "%s: %s" % (fmt, msg)
