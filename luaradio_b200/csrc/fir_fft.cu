@@ -296,6 +296,238 @@ int launch_fft(const FftArgs& base_args, long long n_int, long long n_edge, cuda
     return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Long filters (513 < M <= 8192): uniformly partitioned overlap-save with a frequency-domain delay line.
+// The taps are cut into P partitions of 512; with hop 512 and N = 1024 every input block is transformed ONCE,
+//     Y_b = sum_p X_{b-p} * H_p,      y[512 b + j] = IFFT(Y_b)[512 + j],  j < 512,
+// so a block costs one forward FFT, P spectrum multiply-accumulates and one inverse FFT (the old scheme ran P full
+// passes over memory: P forward + P inverse transforms and P-1 read-modify-writes of y).  A CTA owns a contiguous
+// run of blocks; its FD_W warps transform FD_W consecutive blocks, park the spectra in a shared-memory ring of
+// FD_W + P - 1 slots (register layout [k2][lane], so no transposition and no bank conflicts), and after one CTA
+// barrier each warp accumulates the spectra of its own and the P-1 previous blocks.  The ring slots double as the
+// 32x32 transposition tiles of both transforms (a slot is dead between its block leaving the delay line and the next
+// block landing in it), so a CTA needs 8 + 8.25 (FD_W + P - 1) KB and two CTAs fit per SM.  The run starts with one
+// group that only fills the ring (P-1 redundant transforms per ~1800 blocks).  P <= 4 per launch (ring = 91 KB);
+// longer filters run ceil(P/4) launches, the later ones accumulating into y.
+// ---------------------------------------------------------------------------------------------
+constexpr int FD_W = 8;
+constexpr int FD_MAXPC = 4;
+constexpr int FD_HOP = 512;
+
+struct FdlArgs {
+    const float2* x;
+    const float2* hist;
+    float2* y;
+    const float2* H;          // pc tap spectra [p][k2][k1], already scaled by 1/N
+    const float2* tw;
+    long long n;
+    long long b_lo, b_hi, nblocks, chunk;
+    int pc;                   // partitions handled by this launch
+    int hist_len;
+    int in_shift;             // 512 * index of the first partition of this launch
+    int accumulate;
+};
+
+template <bool EDGE, int PC>
+__global__ void __launch_bounds__(FD_W * 32, 2)
+fir_fft_fdl_kernel(const __grid_constant__ FdlArgs A) {
+    extern __shared__ __align__(16) float2 sm[];
+    float2* s_tw = sm;
+    float2* ring = sm + FF_N;                              // R slots of FF_XCH float2 (padded 32x33 tile / [k2][lane] spectrum)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < FF_N; i += FD_W * 32) s_tw[i] = A.tw[i];
+    constexpr int R = FD_W + PC - 1;                        // compile-time: slot arithmetic folds to constants
+    long long r0, r1;
+    if constexpr (EDGE) {
+        if (blockIdx.x == 0) { r0 = 0; r1 = A.b_lo; } else { r0 = A.b_hi; r1 = A.nblocks; }
+    } else {
+        r0 = A.b_lo + (long long)blockIdx.x * A.chunk;
+        r1 = r0 + A.chunk < A.b_hi ? r0 + A.chunk : A.b_hi;
+    }
+    if (r0 >= r1) return;
+    const long long rbase = r0 - (PC - 1);
+    const long long n = A.n;
+    const int nrel = (int)(r1 - rbase);                     // blocks of this run, relative to rbase: [0, PC-1) only fill the ring
+    const float2* xrun = A.x + ((rbase - 1) * FD_HOP - A.in_shift) + lane;      // interior: never dereferenced out of range
+    float2* yrun = A.y + rbase * FD_HOP + lane;
+    __syncthreads();
+    // slot of block rel: rel mod R.  The slot a warp transposes through in the forward pass is the one its
+    // spectrum then lives in; for the inverse pass it borrows the slot of block rel + FD_W (== block rel - PC + 1, dead
+    // once every warp has finished its multiply-accumulate), which is also the slot it owns in the next group.
+    for (int g = PC - 1 - FD_W; g < nrel; g += FD_W) {
+        const int rel = g + warp;
+        const bool fwd = rel >= 0 && rel < nrel;            // warp-uniform
+        const bool emit = rel >= PC - 1 && rel < nrel;
+        float2 v[32];
+        if (fwd) {
+            float2* xch = ring + (rel % R) * FF_XCH;
+            if constexpr (!EDGE) {
+                const float2* xb = xrun + (long long)rel * FD_HOP;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = __ldcs(xb + 32 * r);
+            } else {
+                const int HL = A.hist_len;
+                const long long base = (rbase + rel - 1) * FD_HOP - A.in_shift;
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const long long i = base + 32 * r + lane;
+                    v[r] = (i >= 0) ? (i < n ? __ldg(A.x + i) : make_float2(0.f, 0.f))
+                                    : ((HL + i >= 0) ? __ldg(A.hist + (HL + i)) : make_float2(0.f, 0.f));
+                }
+            }
+            fft32_nat2br<false>(v);
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                float2 t = v[bitrev5(k1)];
+                if (k1 > 0) t = cmul_conj_if(t, s_tw[k1 * 32 + lane], false);
+                xch[k1 * FF_XSTRIDE + lane] = t;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = xch[lane * FF_XSTRIDE + r];
+            fft32_nat2br<false>(v);                        // X[lane + 32 k2] in v[bitrev5(k2)]
+            __syncwarp();                                  // tile reads done before the spectrum overwrites it
+            float4* sp = reinterpret_cast<float4*>(xch) + lane;           // [k2/2][lane] pairs: 128-bit, conflict-free
+#pragma unroll
+            for (int k2 = 0; k2 < 32; k2 += 2)
+                sp[(k2 / 2) * 32] = make_float4(v[bitrev5(k2)].x, v[bitrev5(k2)].y, v[bitrev5(k2 + 1)].x, v[bitrev5(k2 + 1)].y);
+        }
+        __syncthreads();                                   // the spectra of this group are in the ring
+        if (g >= PC - 1) {
+            // Multiply-accumulate, split by FREQUENCY: warp w owns bins k2 = 4w .. 4w+3 (two 128-bit rows of every slot)
+            // for all FD_W blocks of the group, so a tap-spectrum value is loaded once per group instead of once per
+            // block, and each delay-line value once instead of PC times.  Y_j lands in the slot of block j - (PC-1),
+            // which leaves the delay line after this group; only this warp touches these rows in this phase.
+            if constexpr (!EDGE) {
+                // pull the next group's input block towards L2 while this group multiplies and inverts
+                if (rel + FD_W < nrel) {
+                    const char* nx = reinterpret_cast<const char*>(xrun - lane + (long long)(rel + FD_W) * FD_HOP) + lane * 256;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
+                }
+            }
+            const int s0 = (g - (FD_MAXPC - 1) + R * 4) % R;   // slot of block g - 3 (blocks before g - (PC-1) are never read)
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int row = (2 * warp + half) * 32 + lane;
+                const float4* ring4 = reinterpret_cast<const float4*>(ring);
+                float4 Hr[FD_MAXPC];
+#pragma unroll
+                for (int pp = 0; pp < FD_MAXPC; ++pp)
+                    if (pp < PC) Hr[pp] = __ldg(reinterpret_cast<const float4*>(A.H) + pp * (FF_N / 2) + row);
+                float4 Xr[FD_W + FD_MAXPC - 1];
+                int sl = s0;
+#pragma unroll
+                for (int i = 0; i < FD_W + FD_MAXPC - 1; ++i) {
+                    if (i >= FD_MAXPC - PC) Xr[i] = ring4[sl * (FF_XCH / 2) + row];
+                    sl = sl + 1 == R ? 0 : sl + 1;
+                }
+                int so = (g + FD_W) % R;
+#pragma unroll
+                for (int j = 0; j < FD_W; ++j) {
+                    if (g + j < nrel) {
+                        float4 a = Xr[j + FD_MAXPC - 1];
+                        float2 t0 = __fmul2_rn(make_float2(-a.y, a.x), make_float2(Hr[0].y, Hr[0].y));
+                        float2 ye = __ffma2_rn(make_float2(a.x, a.y), make_float2(Hr[0].x, Hr[0].x), t0);
+                        float2 t1 = __fmul2_rn(make_float2(-a.w, a.z), make_float2(Hr[0].w, Hr[0].w));
+                        float2 yo = __ffma2_rn(make_float2(a.z, a.w), make_float2(Hr[0].z, Hr[0].z), t1);
+#pragma unroll
+                        for (int pp = 1; pp < FD_MAXPC; ++pp) {
+                            if (pp < PC) {
+                                a = Xr[j + FD_MAXPC - 1 - pp];
+                                ye = __ffma2_rn(make_float2(a.x, a.y), make_float2(Hr[pp].x, Hr[pp].x), ye);
+                                ye = __ffma2_rn(make_float2(-a.y, a.x), make_float2(Hr[pp].y, Hr[pp].y), ye);
+                                yo = __ffma2_rn(make_float2(a.z, a.w), make_float2(Hr[pp].z, Hr[pp].z), yo);
+                                yo = __ffma2_rn(make_float2(-a.w, a.z), make_float2(Hr[pp].w, Hr[pp].w), yo);
+                            }
+                        }
+                        reinterpret_cast<float4*>(ring)[so * (FF_XCH / 2) + row] = make_float4(ye.x, ye.y, yo.x, yo.y);
+                    }
+                    so = so + 1 == R ? 0 : so + 1;
+                }
+            }
+        }
+        __syncthreads();                                   // every Y_b is in the slot its owner transposes through next
+        if (emit) {
+            float2* xch = ring + ((rel + FD_W) % R) * FF_XCH;
+            {
+                const float4* yp = reinterpret_cast<const float4*>(xch) + lane;
+#pragma unroll
+                for (int k2 = 0; k2 < 32; k2 += 2) {
+                    const float4 t = yp[(k2 / 2) * 32];
+                    v[bitrev5(k2)] = make_float2(t.x, t.y);
+                    v[bitrev5(k2 + 1)] = make_float2(t.z, t.w);
+                }
+            }
+            __syncwarp();                                  // Y is in registers before the slot becomes the transposition tile
+            fft32_br2nat<true>(v);
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                float2 t = v[n2];
+                if (n2 > 0) t = cmul_conj_if(t, s_tw[n2 * 32 + lane], true);
+                xch[n2 * FF_XSTRIDE + lane] = t;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = xch[lane * FF_XSTRIDE + r];
+            __syncwarp();
+            fft32_nat2br<true>(v);                         // y-block sample lane + 32 n1 in v[bitrev5(n1)]
+            float2* yb = yrun + (long long)rel * FD_HOP;
+            const long long o0 = (rbase + rel) * FD_HOP + lane;
+#pragma unroll
+            for (int n1 = 16; n1 < 32; ++n1) {
+                if (!EDGE || o0 + 32 * (n1 - 16) < n) {
+                    float2 t = v[bitrev5(n1)];
+                    if (A.accumulate) t = __fadd2_rn(t, yb[32 * (n1 - 16)]);
+                    __stcs(yb + 32 * (n1 - 16), t);
+                }
+            }
+        }
+    }
+}
+
+template <int PC>
+int launch_fdl_pc(FdlArgs a, cudaStream_t s) {
+    static bool configured = false;
+    constexpr size_t smem = (size_t)(FF_N + (FD_W + PC - 1) * FF_XCH) * sizeof(float2);
+    auto ki = fir_fft_fdl_kernel<false, PC>;
+    auto ke = fir_fft_fdl_kernel<true, PC>;
+    if (!configured) {
+        LRB_CHECK(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LRB_CHECK(cudaFuncSetAttribute(ke, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long n_int = a.b_hi - a.b_lo;
+    const bool edges = a.b_lo > 0 || a.nblocks > a.b_hi;
+    cudaStream_t side = (n_int > 0 && edges) ? side_fork(s) : s;
+    if (edges) {
+        ke<<<2, FD_W * 32, smem, side>>>(a);
+        count_launch();
+    }
+    if (n_int > 0) {
+        long long ctas = (n_int + FD_W - 1) / FD_W;
+        if (ctas > 2LL * ctx().sm_count) ctas = 2LL * ctx().sm_count;
+        long long chunk = (n_int + ctas - 1) / ctas;
+        chunk = (chunk + FD_W - 1) / FD_W * FD_W;
+        ctas = (n_int + chunk - 1) / chunk;
+        a.chunk = chunk;
+        ki<<<(unsigned)ctas, FD_W * 32, smem, s>>>(a);
+        count_launch();
+    }
+    side_join(s, side);
+    LRB_CHECK(cudaGetLastError());
+    return 1;
+}
+
+int launch_fdl(const FdlArgs& a, cudaStream_t s) {
+    switch (a.pc) {
+        case 1: return launch_fdl_pc<1>(a, s);
+        case 2: return launch_fdl_pc<2>(a, s);
+        case 3: return launch_fdl_pc<3>(a, s);
+        default: return launch_fdl_pc<4>(a, s);
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -344,7 +576,9 @@ int FirBlock::fast_init() {
             for (int m = 0; m < mc; ++m) acc += h[m0 + m] * wtab[(int)(((long long)k * m) % FF_N)];
             acc /= (double)FF_N;
             const int k1 = k % 32, k2 = k / 32;
-            H[(size_t)part * FF_N + k2 * 32 + k1] = make_float2((float)acc.real(), (float)acc.imag());
+            // single block: [k2][k1]; partitioned (delay-line kernel): [k2/2][k1][k2&1] for 128-bit loads
+            const size_t at = long_filter ? (size_t)(k2 / 2) * 64 + k1 * 2 + (k2 & 1) : (size_t)k2 * 32 + k1;
+            H[(size_t)part * FF_N + at] = make_float2((float)acc.real(), (float)acc.imag());
         }
     }
     for (int a = 0; a < 32; ++a)
@@ -419,6 +653,23 @@ int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long
     // blocks of L outputs; in packed-real mode one FFT covers two of them
     const long long per = (fast->in_mode == 1) ? 2LL * L : (long long)L;
     const long long nblocks = ((long long)n + per - 1) / per;
+    if (fast->nparts > 1) {
+        // frequency-domain delay line: hop 512, blocks b cover outputs [512 b, 512 b + 512)
+        const long long nb = ((long long)n + FD_HOP - 1) / FD_HOP;
+        for (int p0 = 0; p0 < fast->nparts; p0 += FD_MAXPC) {
+            FdlArgs a;
+            a.x = (const float2*)dx; a.hist = (const float2*)d_hist[cur]; a.y = (float2*)dy;
+            a.H = fast->d_H + (size_t)p0 * FF_N; a.tw = fast->d_tw; a.n = (long long)n;
+            a.pc = std::min(FD_MAXPC, fast->nparts - p0);
+            a.nblocks = nb;
+            a.b_lo = std::min<long long>(nb, a.pc + p0);          // first block whose ring pre-fill reads x[>= 0]
+            a.b_hi = std::max<long long>(a.b_lo, (long long)n / FD_HOP);
+            if (a.b_hi > nb) a.b_hi = nb;
+            a.chunk = 0; a.hist_len = M - 1; a.in_shift = p0 * FD_HOP; a.accumulate = p0 > 0 ? 1 : 0;
+            if (launch_fdl(a, s) < 0) return -1;
+        }
+        return 1;
+    }
     for (int part = 0; part < fast->nparts; ++part) {
         const int shift = part * Mp;
         // interior blocks [b_lo, b_hi): b*per - (Mp-1) - shift >= 0  and  (b+1)*per <= n

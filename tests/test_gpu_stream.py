@@ -320,3 +320,25 @@ def test_wbfm_chain_from_u8_iq_file():
     ref = O.wbfm_mono_chain().process(O.iq_file_convert(u8, "u8"))
     close(snk.result(), ref)
     assert top.describe_gpu_graph().startswith("iqconv(u8) | tuner+discrim")
+
+
+@pytest.mark.parametrize("M", [514, 1025, 1536, 2048, 2049, 4097, 8192])
+@pytest.mark.parametrize("kind", ["crcf", "cccf"])
+def test_long_fir_partitioned_overlap_save(M, kind):
+    """Filters longer than one FFT block allows run the partitioned overlap-save kernel (frequency-domain delay line):
+    interior runs across many CTAs, ring wrap-around, head/tail runs against the carried history, accumulate launches
+    for more than 4 partitions."""
+    rng = np.random.default_rng(M + len(kind))
+    n = 700000
+    taps = rng.uniform(-1, 1, M)
+    if kind == "cccf":
+        taps = taps + 1j * rng.uniform(-1, 1, M)
+    taps = (taps / np.sum(np.abs(taps))).astype(np.complex64 if kind == "cccf" else np.float32)
+    x = rnd_c(rng, n)
+    blk = mk(radio.FIRFilterBlock, [(ComplexFloat32 if kind == "cccf" else Float32).vector_from_array(taps), True], ComplexFloat32)
+    cuts = [(0, 300001), (300001, 300013), (300013, 304000), (304000, n)]
+    got = stream(blk, x, cuts)
+    import scipy.signal
+    ref = scipy.signal.fftconvolve(x.astype(np.complex128), taps.astype(np.complex128))[:n].astype(np.complex64)
+    close(got, ref)
+    blk.cleanup()

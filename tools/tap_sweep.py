@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=1 << 30)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--taps", default="16,64,128,512,2048", help="comma-separated tap counts")
     args = ap.parse_args()
     import torch
     import luaradio_b200 as radio
@@ -35,7 +36,7 @@ def main():
     _lib.check(lib.lrb200_synth_white_iq(ctypes.c_void_p(x.data_ptr()), 0, n, 1))
     peak, src = bench.peaks()
     rows = []
-    for M in (16, 64, 128, 512, 2048):
+    for M in [int(t) for t in args.taps.split(",")]:
         taps = np.array(radio.filter_utils.firwin_lowpass(M, 0.25), np.float32)
         for kind in ("crcf", "cccf"):
             if kind == "crcf":
