@@ -163,6 +163,15 @@ lrb200_block_t* lrb200_c2r_create(unsigned flags);
  * output: ComplexFloat32.  As the first stage of a graph it makes the host->device copy carry the file bytes
  * (2 B/sample for u8 instead of 8).  Unknown format -> NULL with "Unsupported format". */
 lrb200_block_t* lrb200_iqconv_create(const char* format, unsigned flags);
+/* RealFileSource (radio/blocks/sources/realfile.lua:86-104): one component per sample -> Float32. */
+lrb200_block_t* lrb200_realconv_create(const char* format, unsigned flags);
+/* The sink boundary: ComplexFloat32 -> interleaved I/Q (IQFileSink:process, radio/blocks/sinks/iqfile.lua:66-80) and
+ * Float32 -> real samples (RealFileSink, radio/blocks/sinks/realfile.lua; WAVFileSink:process, sinks/wavfile.lua:170-186
+ * with "u8" / "s16le" / "s32le" for 8 / 16 / 32 bits per sample): raw = x * scale + offset in double, truncated toward
+ * zero into the C integer type, then the byte swap.  As the last stage of a graph the device->host copy carries the
+ * file's bytes.  Inputs outside [-1, 1] saturate (undefined in the reference). */
+lrb200_block_t* lrb200_iqsink_create(const char* format, unsigned flags);
+lrb200_block_t* lrb200_realsink_create(const char* format, unsigned flags);
 
 /* ---- GPU flow graph: connected GPU blocks on one stream with device-resident buffers ----------
  * Replaces, for a connected run of GPU blocks, the fork-per-block + socketpair plumbing of

@@ -59,6 +59,9 @@ _PROTOS = {
     "lrb200_cmag_create": (c_void_p, [c_uint]),
     "lrb200_c2r_create": (c_void_p, [c_uint]),
     "lrb200_iqconv_create": (c_void_p, [c_char_p, c_uint]),
+    "lrb200_realconv_create": (c_void_p, [c_char_p, c_uint]),
+    "lrb200_iqsink_create": (c_void_p, [c_char_p, c_uint]),
+    "lrb200_realsink_create": (c_void_p, [c_char_p, c_uint]),
     "lrb200_graph_create": (c_void_p, []),
     "lrb200_graph_append": (c_int, [c_void_p, c_void_p]),
     "lrb200_graph_commit": (c_int, [c_void_p, c_int]),

@@ -53,6 +53,10 @@ class IQFileSource(Block):
     scale; iqfile.lua:96-108) runs on the GPU: process() converts one chunk through the C ABI; inside a GPU flow
     graph the converter becomes the graph's first stage and the RAW bytes cross PCIe (2 B/sample for "u8")."""
     name = "IQFileSource"
+    raw_source = True                      # CompositeBlock: feed the graph read_raw() bytes, converter = stage 0
+    components = 2
+    create_fn = "lrb200_iqconv_create"
+    out_type = ComplexFloat32
     FORMATS = {"u8": 1, "s8": 1, "u16le": 2, "u16be": 2, "s16le": 2, "s16be": 2, "u32le": 4, "u32be": 4,
                "s32le": 4, "s32be": 4, "f32le": 4, "f32be": 4, "f64le": 8, "f64be": 8}
 
@@ -62,10 +66,10 @@ class IQFileSource(Block):
         assert format in self.FORMATS, 'Unsupported format ("%s")' % format
         assert rate is not None, "Missing argument #3 (rate)"
         self.file, self.format, self.rate, self.repeat_on_eof = file, format, float(rate), repeat_on_eof
-        self.sample_bytes = 2 * self.FORMATS[format]
+        self.sample_bytes = self.components * self.FORMATS[format]
         self.chunk_size = int(chunk)          # samples per read; the reference uses 8192 (iqfile.lua:52)
         self._handle = None
-        self.add_type_signature([], [Output("out", ComplexFloat32)])
+        self.add_type_signature([], [Output("out", self.out_type)])
 
     def get_rate(self):
         return self.rate
@@ -78,7 +82,7 @@ class IQFileSource(Block):
         else:
             self._buf = np.frombuffer(self.file.read(), np.uint8)
         self._pos = 0
-        self.out = ComplexFloat32.vector()
+        self.out = self.out_type.vector()
 
     def read_raw(self):
         """Next chunk of raw file bytes (whole samples), or None at EOF."""
@@ -94,7 +98,7 @@ class IQFileSource(Block):
 
     def make_device_handle(self):
         lib = _lib.require_device()
-        return _lib.check_handle(lib.lrb200_iqconv_create(self.format.encode(), _lib.LRB200_DEVICE), "lrb200 iqconv object")
+        return _lib.check_handle(getattr(lib, self.create_fn)(self.format.encode(), _lib.LRB200_DEVICE), "lrb200 file-format object")
 
     def process(self):
         raw = self.read_raw()
@@ -102,17 +106,205 @@ class IQFileSource(Block):
             return None
         lib = _lib.require_device()
         if self._handle is None:
-            self._handle = _lib.check_handle(lib.lrb200_iqconv_create(self.format.encode(), _lib.LRB200_HOST), "lrb200 iqconv object")
+            self._handle = _lib.check_handle(getattr(lib, self.create_fn)(self.format.encode(), _lib.LRB200_HOST), "lrb200 file-format object")
         n = len(raw) // self.sample_bytes
         out = self.out.resize(n)
         n_out = ctypes.c_size_t(0)
-        _lib.check(lib.lrb200_block_execute(self._handle, raw.ctypes.data, n, out.ctypes_ptr(), ctypes.byref(n_out)), "iqconv")
+        _lib.check(lib.lrb200_block_execute(self._handle, raw.ctypes.data, n, out.ctypes_ptr(), ctypes.byref(n_out)), "file-format conversion")
         return out.resize(n_out.value)
 
     def cleanup(self):
         if self._handle:
             _lib.load().lrb200_block_destroy(self._handle)
             self._handle = None
+
+
+class RealFileSource(IQFileSource):
+    """radio/blocks/sources/realfile.lua:27-110: real samples in one of the 14 formats -> Float32, converted on the GPU."""
+    name = "RealFileSource"
+    components = 1
+    create_fn = "lrb200_realconv_create"
+    out_type = Float32
+
+
+class RawFileSource(Block):
+    """radio/blocks/sources/rawfile.lua:75-108: a file of raw `data_type` elements (host byte order) -> that type.
+    Pure I/O: in a GPU flow graph the chunks go straight into the graph's pinned H2D staging."""
+    name = "RawFileSource"
+
+    def instantiate(self, file, data_type, rate, repeat_on_eof=False, chunk=8192):
+        assert file is not None, "Missing argument #1 (file)"
+        assert data_type is not None, "Missing argument #2 (data_type)"
+        assert rate is not None, "Missing argument #3 (rate)"
+        self.file, self.data_type, self.rate, self.repeat_on_eof, self.chunk_size = file, data_type, float(rate), repeat_on_eof, int(chunk)
+        self.add_type_signature([], [Output("out", data_type)])
+
+    def get_rate(self):
+        return self.rate
+
+    def initialize(self):
+        dt = self.data_type.dtype
+        if isinstance(self.file, str):
+            self._buf = np.fromfile(self.file, dt)
+        else:
+            b = self.file if isinstance(self.file, (bytes, bytearray, memoryview)) else self.file.read()
+            self._buf = np.frombuffer(bytes(b)[:len(b) // dt.itemsize * dt.itemsize], dt)
+        self._pos = 0
+
+    def process(self):
+        if self._pos >= len(self._buf):
+            if not self.repeat_on_eof or len(self._buf) == 0:
+                return None
+            self._pos = 0
+        x = self._buf[self._pos:self._pos + self.chunk_size]
+        self._pos += len(x)
+        return Vector.cast(np.ascontiguousarray(x))
+
+
+class _FileSinkBase(Block):
+    """Shared by IQFileSink / RealFileSink / WAVFileSink: float samples -> the file's sample format on the GPU
+    (lrb200_iqsink_create / lrb200_realsink_create).  process() converts one chunk through the C ABI; as the sink of a GPU
+    flow graph the converter is the graph's last stage and write_raw() receives the file bytes from the D2H copy."""
+    raw_sink = True
+    components = 1
+    create_fn = "lrb200_realsink_create"
+    in_type = Float32
+    FORMATS = IQFileSource.FORMATS
+
+    def _setup(self, file, format):
+        assert file is not None, "Missing argument #1 (file)"
+        assert format in self.FORMATS, 'Unsupported format ("%s")' % format
+        self.file, self.format = file, format
+        self.raw_sample_bytes = self.components * self.FORMATS[format]
+        self._handle, self._fh, self._own = None, None, False
+        self.count = 0
+
+    def initialize(self):
+        if isinstance(self.file, str):
+            self._fh, self._own = open(self.file, "wb"), True
+        else:
+            self._fh = self.file
+
+    def make_device_handle(self):
+        lib = _lib.require_device()
+        return _lib.check_handle(getattr(lib, self.create_fn)(self.format.encode(), _lib.LRB200_DEVICE), "lrb200 file-format object")
+
+    def convert(self, x):
+        """samples (numpy / Vector) -> file bytes (uint8 array), through the C ABI in host-pointer mode."""
+        lib = _lib.require_device()
+        if self._handle is None:
+            self._handle = _lib.check_handle(getattr(lib, self.create_fn)(self.format.encode(), _lib.LRB200_HOST), "lrb200 file-format object")
+        a = np.ascontiguousarray(x.data if isinstance(x, Vector) else x, dtype=self.in_type.dtype)
+        raw = np.zeros(len(a) * self.raw_sample_bytes, np.uint8)
+        n_out = ctypes.c_size_t(0)
+        _lib.check(lib.lrb200_block_execute(self._handle, a.ctypes.data, len(a), raw.ctypes.data, ctypes.byref(n_out)), "file-format conversion")
+        return raw
+
+    def write_raw(self, raw, num_samples):
+        self.count += num_samples
+        self._fh.write(raw.tobytes())
+
+    def process(self, x):
+        self.write_raw(self.convert(x), x.length)
+
+    def cleanup(self):
+        if self._handle:
+            _lib.load().lrb200_block_destroy(self._handle)
+            self._handle = None
+        if self._fh is not None:
+            self._fh.flush()
+            if self._own:
+                self._fh.close()
+            self._fh = None
+
+
+class IQFileSink(_FileSinkBase):
+    """radio/blocks/sinks/iqfile.lua:25-100: ComplexFloat32 -> interleaved I/Q in one of the 14 formats."""
+    name = "IQFileSink"
+    components = 2
+    create_fn = "lrb200_iqsink_create"
+    in_type = ComplexFloat32
+
+    def instantiate(self, file, format):
+        self._setup(file, format)
+        self.add_type_signature([Input("in", ComplexFloat32)], [])
+
+
+class RealFileSink(_FileSinkBase):
+    """radio/blocks/sinks/realfile.lua: Float32 -> real samples in one of the 14 formats."""
+    name = "RealFileSink"
+
+    def instantiate(self, file, format):
+        self._setup(file, format)
+        self.add_type_signature([Input("in", Float32)], [])
+
+
+class RawFileSink(Block):
+    """radio/blocks/sinks/rawfile.lua:60-67: any type, raw element bytes (host byte order).  Pure I/O."""
+    name = "RawFileSink"
+
+    def instantiate(self, file):
+        assert file is not None, "Missing argument #1 (file)"
+        self.file = file
+        self.add_type_signature([Input("in", lambda t: True)], [])
+
+    def initialize(self):
+        self._own = isinstance(self.file, str)
+        self._fh = open(self.file, "wb") if self._own else self.file
+
+    def process(self, x):
+        self._fh.write(np.ascontiguousarray(x.data).tobytes())
+
+    def cleanup(self):
+        self._fh.flush()
+        if self._own:
+            self._fh.close()
+
+
+class WAVFileSink(_FileSinkBase):
+    """radio/blocks/sinks/wavfile.lua:58-225: Float32 channel(s) -> PCM WAV (8/16/32 bits = u8/s16le/s32le).  The 44-byte
+    RIFF/fmt/data headers are written on cleanup() with the final sizes (:196-218).  One channel: the conversion is the
+    last stage of the GPU flow graph; two or more: channels are interleaved on the host, then converted."""
+    name = "WAVFileSink"
+    WAVE_FORMATS = {8: "u8", 16: "s16le", 32: "s32le"}
+
+    def instantiate(self, file, num_channels, bits_per_sample=16):
+        assert num_channels is not None, "Missing argument #2 (num_channels)"
+        assert bits_per_sample in self.WAVE_FORMATS, "Unsupported bits per sample (%s)" % str(bits_per_sample)
+        self._setup(file, self.WAVE_FORMATS[bits_per_sample])
+        self.num_channels, self.bits_per_sample = int(num_channels), bits_per_sample
+        self.raw_sink = self.num_channels == 1
+        if self.num_channels == 1:
+            self.add_type_signature([Input("in", Float32)], [])
+        else:
+            self.add_type_signature([Input("in%d" % (i + 1), Float32) for i in range(self.num_channels)], [])
+
+    def header(self):
+        import struct
+        bps = self.bits_per_sample // 8
+        data, rate = self.count * self.num_channels * bps, int(self.get_rate())
+        return (b"RIFF" + struct.pack("<I", 36 + data) + b"WAVE" + b"fmt " +
+                struct.pack("<IHHIIHH", 16, 1, self.num_channels, rate, rate * self.num_channels * bps,
+                            self.num_channels * bps, self.bits_per_sample) + b"data" + struct.pack("<I", data))
+
+    def initialize(self):
+        _FileSinkBase.initialize(self)
+        self._fh.write(b"\0" * 44)            # seek past the headers for now (wavfile.lua:162-165)
+
+    def process(self, *channels):
+        if self.num_channels == 1:
+            return _FileSinkBase.process(self, channels[0])
+        n = channels[0].length
+        inter = np.stack([np.asarray(c.data[:n], np.float32) for c in channels], axis=1).reshape(-1)
+        self.count += n
+        self._fh.write(self.convert(inter).tobytes())
+
+    def cleanup(self):
+        if self._fh is not None:
+            self._fh.seek(0)
+            self._fh.write(self.header())
+            self._fh.seek(0, 2)
+        _FileSinkBase.cleanup(self)
 
 
 class ArraySink(Block):
@@ -309,17 +501,21 @@ class CompositeBlock(Block):
         lib = _lib.require_device()
         source, sink, blocks = chain[0], chain[-1], chain[1:-1]
         g = _lib.check_handle(lib.lrb200_graph_create(), "lrb200 graph")
-        raw_source = isinstance(source, IQFileSource)
+        raw_source = bool(getattr(source, "raw_source", False))
+        raw_sink = bool(getattr(sink, "raw_sink", False))
         try:
             if raw_source:      # the file's sample format is converted on the device, as the first graph stage
                 _lib.check(lib.lrb200_graph_append(g, source.make_device_handle()), "graph_append(iqconv)")
             for b in blocks:
                 h = b.make_device_handle()
                 _lib.check(lib.lrb200_graph_append(g, h), "graph_append(%s)" % b.name)
+            if raw_sink:        # ... and the sink's file format is produced on the device, as the last stage
+                _lib.check(lib.lrb200_graph_append(g, sink.make_device_handle()), "graph_append(file sink)")
             _lib.check(lib.lrb200_graph_commit(g, 1 if fuse else 0), "graph_commit")
             self._gpu_desc = lib.lrb200_graph_describe(g).decode()
             out_type = blocks[-1].get_output_type()
             out = out_type.vector()
+            raw_out = np.zeros(0, np.uint8)
             while True:
                 if raw_source:
                     raw = source.read_raw()
@@ -331,8 +527,15 @@ class CompositeBlock(Block):
                     if x is None:
                         break
                     n_in, in_ptr = x.length, x.ctypes_ptr()
-                out.resize(lib.lrb200_graph_max_output(g, n_in))
                 n_out = ctypes.c_size_t(0)
+                if raw_sink:
+                    need = lib.lrb200_graph_max_output(g, n_in) * sink.raw_sample_bytes
+                    if len(raw_out) < need:
+                        raw_out = np.zeros(need, np.uint8)
+                    _lib.check(lib.lrb200_graph_execute(g, in_ptr, n_in, raw_out.ctypes.data, ctypes.byref(n_out)), "graph_execute")
+                    sink.write_raw(raw_out[:n_out.value * sink.raw_sample_bytes], n_out.value)
+                    continue
+                out.resize(lib.lrb200_graph_max_output(g, n_in))
                 _lib.check(lib.lrb200_graph_execute(g, in_ptr, n_in, out.ctypes_ptr(), ctypes.byref(n_out)), "graph_execute")
                 out.resize(n_out.value)
                 sink.process(out)

@@ -152,6 +152,8 @@ int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist
 // tuner.cu: fused FrequencyTranslator -> FIR(crcf) -> Downsampler; returns nullptr (with the error set) on failure
 // iqconv.cu: IQFileSource sample format -> ComplexFloat32 (nullptr + error for an unknown format)
 Block* make_iqconv(const char* format, bool dev);
+// RealFileSource (to_file = false, comps = 1), RealFileSink/WAVFileSink (true, 1), IQFileSink (true, 2)
+Block* make_fileconv(const char* format, bool to_file, int comps, bool dev);
 // disc_gain != 0 additionally fuses a FrequencyDiscriminator(gain) behind it (float output)
 Block* make_tuner(double turns_per_sample, const float* taps, int ntaps, int decim, float disc_gain);
 }  // namespace lrb

@@ -579,6 +579,22 @@ lrb200_block_t* lrb200_iqconv_create(const char* format, unsigned flags) {
     return wrap(b);
 }
 
+lrb200_block_t* lrb200_realconv_create(const char* format, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    Block* b = make_fileconv(format, false, 1, (flags & LRB200_DEVICE) != 0);
+    return b ? wrap(b) : nullptr;
+}
+lrb200_block_t* lrb200_iqsink_create(const char* format, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    Block* b = make_fileconv(format, true, 2, (flags & LRB200_DEVICE) != 0);
+    return b ? wrap(b) : nullptr;
+}
+lrb200_block_t* lrb200_realsink_create(const char* format, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    Block* b = make_fileconv(format, true, 1, (flags & LRB200_DEVICE) != 0);
+    return b ? wrap(b) : nullptr;
+}
+
 // ---- synthetic sources -------------------------------------------------------------------------
 int lrb200_synth_white_iq(complex_float32_t* dst, uint64_t n0, size_t n, uint32_t seed) {
     if (ensure_init() != 0) return -1;

@@ -7,7 +7,9 @@
 #include "common.cuh"
 #include "blocks.h"
 
+#include <algorithm>
 #include <cstring>
+#include <string>
 #include <new>
 
 namespace lrb {
@@ -137,6 +139,143 @@ struct IqConvBlock : Block {
     }
 };
 
+
+// ---- RealFileSource (radio/blocks/sources/realfile.lua:86-104): the same per-component map, one component per sample
+template <int FMT, bool SWAP, int BYTES>
+__global__ void __launch_bounds__(256)
+realconv_kernel(const unsigned char* __restrict__ x, float* __restrict__ y, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        y[i] = conv_one<FMT, SWAP>(x + i * BYTES);
+}
+
+// ---- Sink boundary: Float32 / ComplexFloat32 -> file sample format, on the device, so that the D2H copy carries the
+// file's bytes (2 B/sample for 16-bit WAV instead of 4).  Reference: IQFileSink:process (radio/blocks/sinks/iqfile.lua:
+// 66-80), RealFileSink (sinks/realfile.lua), WAVFileSink:process (sinks/wavfile.lua:170-186): raw = x*scale + offset in
+// double, stored into the C integer type (truncation toward zero), then the byte swap.  Values outside [-1, 1] are
+// undefined behaviour in the reference's double -> integer store; here they saturate.
+template <int BYTES> struct RawT;
+template <> struct RawT<1> { typedef uint8_t type; };
+template <> struct RawT<2> { typedef uint16_t type; };
+template <> struct RawT<4> { typedef uint32_t type; };
+template <> struct RawT<8> { typedef uint64_t type; };
+
+template <int FMT, bool SWAP>
+__device__ __forceinline__ typename RawT<(FMT == F_U8 || FMT == F_S8) ? 1 : (FMT == F_U16 || FMT == F_S16) ? 2 : (FMT == F_F64 ? 8 : 4)>::type
+sink_one(float xf) {
+    constexpr double scale = (FMT == F_U8 || FMT == F_S8) ? 127.5 : (FMT == F_U16 || FMT == F_S16) ? 32767.5
+                             : (FMT == F_U32 || FMT == F_S32) ? 2147483647.5 : 1.0;
+    constexpr double offset = FMT == F_U8 ? 127.5 : FMT == F_U16 ? 32767.5 : FMT == F_U32 ? 2147483647.5 : 0.0;
+    const double v = __dadd_rn(__dmul_rn((double)xf, scale), offset);
+    if constexpr (FMT == F_F32) { uint32_t b = __float_as_uint((float)v); return SWAP ? bswap32(b) : b; }
+    else if constexpr (FMT == F_F64) { uint64_t b = (uint64_t)__double_as_longlong(v); return SWAP ? bswap64(b) : b; }
+    else {
+        long long t = __double2ll_rz(v);
+        constexpr long long lo = FMT == F_S8 ? -128LL : FMT == F_S16 ? -32768LL : FMT == F_S32 ? -2147483648LL : 0LL;
+        constexpr long long hi = FMT == F_U8 ? 255LL : FMT == F_S8 ? 127LL : FMT == F_U16 ? 65535LL : FMT == F_S16 ? 32767LL
+                                 : FMT == F_U32 ? 4294967295LL : 2147483647LL;
+        t = t < lo ? lo : (t > hi ? hi : t);
+        if constexpr (FMT == F_U8 || FMT == F_S8) return (uint8_t)t;
+        else if constexpr (FMT == F_U16 || FMT == F_S16) { uint16_t b = (uint16_t)t; return SWAP ? bswap16(b) : b; }
+        else { uint32_t b = (uint32_t)t; return SWAP ? bswap32(b) : b; }
+    }
+}
+
+template <int BYTES> struct alignas(4 * BYTES) Raw4 { typename RawT<BYTES>::type v[4]; };
+
+// four components per thread: one 128-bit load, one 4*BYTES store; VEC = false: any alignment, one component per thread
+template <int FMT, bool SWAP, int BYTES, bool VEC>
+__global__ void __launch_bounds__(256)
+sinkconv_kernel(const float* __restrict__ x, unsigned char* __restrict__ y, long long n) {
+    typedef typename RawT<BYTES>::type T;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if constexpr (VEC) {
+        const long long n4 = n / 4;
+        for (long long i = tid; i < n4; i += stride) {
+            const float4 v = __ldcs(reinterpret_cast<const float4*>(x) + i);
+            Raw4<BYTES> o;
+            o.v[0] = sink_one<FMT, SWAP>(v.x);
+            o.v[1] = sink_one<FMT, SWAP>(v.y);
+            o.v[2] = sink_one<FMT, SWAP>(v.z);
+            o.v[3] = sink_one<FMT, SWAP>(v.w);
+            reinterpret_cast<Raw4<BYTES>*>(y)[i] = o;
+        }
+        if (tid < n - n4 * 4) reinterpret_cast<T*>(y)[n4 * 4 + tid] = sink_one<FMT, SWAP>(x[n4 * 4 + tid]);
+    } else {
+        for (long long i = tid; i < n; i += stride) {
+            const T b = sink_one<FMT, SWAP>(x[i]);
+            memcpy(y + i * BYTES, &b, BYTES);
+        }
+    }
+}
+
+// direction / arity of the three other file-format blocks
+struct FileConvBlock : Block {
+    FmtInfo info;
+    bool to_file;             // true: float -> raw (sinks); false: raw -> float (RealFileSource)
+    int comps;                // components per sample (1 real, 2 complex)
+    std::string label;
+    FileConvBlock(const FmtInfo& f, bool to_file_, int comps_, bool dev) : info(f), to_file(to_file_), comps(comps_) {
+        label = std::string(to_file ? (comps == 2 ? "iqsink(" : "realsink(") : "realconv(") + f.name + ")";
+        name = label.c_str();
+        in_size = to_file ? 4 * (size_t)comps : (size_t)f.bytes * comps;
+        out_size = to_file ? (size_t)f.bytes * comps : 4 * (size_t)comps;
+        dev_ptrs = dev;
+    }
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override {
+        *n_out = n;
+        consumed += n;
+        if (n == 0) return 0;
+        const long long nc = (long long)n * comps;
+        const int cap = ctx().sm_count * 16;
+        const bool sw = info.big_endian;
+        if (!to_file) {
+            int blocks = (int)std::min<long long>((nc + 255) / 256, cap);
+            const unsigned char* x = (const unsigned char*)dx;
+            float* y = (float*)dy;
+#define LRB_RC(F, B) \
+            if (sw) realconv_kernel<F, true, B><<<blocks, 256, 0, s>>>(x, y, nc); else realconv_kernel<F, false, B><<<blocks, 256, 0, s>>>(x, y, nc)
+            switch (info.fmt) {
+                case F_U8: realconv_kernel<F_U8, false, 1><<<blocks, 256, 0, s>>>(x, y, nc); break;
+                case F_S8: realconv_kernel<F_S8, false, 1><<<blocks, 256, 0, s>>>(x, y, nc); break;
+                case F_U16: LRB_RC(F_U16, 2); break;
+                case F_S16: LRB_RC(F_S16, 2); break;
+                case F_U32: LRB_RC(F_U32, 4); break;
+                case F_S32: LRB_RC(F_S32, 4); break;
+                case F_F32: LRB_RC(F_F32, 4); break;
+                default: LRB_RC(F_F64, 8); break;
+            }
+#undef LRB_RC
+        } else {
+            const float* x = (const float*)dx;
+            unsigned char* y = (unsigned char*)dy;
+            const bool vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) % (4 * info.bytes)) == 0;
+            const long long threads = vec ? std::max<long long>(nc / 4, 4) : nc;
+            int blocks = (int)std::min<long long>((threads + 255) / 256, cap);
+#define LRB_SK2(F, SW, B) \
+            if (vec) sinkconv_kernel<F, SW, B, true><<<blocks, 256, 0, s>>>(x, y, nc); else sinkconv_kernel<F, SW, B, false><<<blocks, 256, 0, s>>>(x, y, nc)
+#define LRB_SK(F, B) \
+            if (sw) { LRB_SK2(F, true, B); } else { LRB_SK2(F, false, B); }
+            switch (info.fmt) {
+                case F_U8: LRB_SK2(F_U8, false, 1); break;
+                case F_S8: LRB_SK2(F_S8, false, 1); break;
+                case F_U16: LRB_SK(F_U16, 2); break;
+                case F_S16: LRB_SK(F_S16, 2); break;
+                case F_U32: LRB_SK(F_U32, 4); break;
+                case F_S32: LRB_SK(F_S32, 4); break;
+                case F_F32: LRB_SK(F_F32, 4); break;
+                default: LRB_SK(F_F64, 8); break;
+            }
+#undef LRB_SK
+#undef LRB_SK2
+        }
+        count_launch();
+        LRB_CHECK(cudaGetLastError());
+        return 0;
+    }
+};
+
 }  // namespace
 
 Block* make_iqconv(const char* format, bool dev) {
@@ -148,6 +287,18 @@ Block* make_iqconv(const char* format, bool dev) {
             return b;
         }
     set_error("Unsupported format (\"%s\")", format);     // iqfile.lua:46
+    return nullptr;
+}
+
+Block* make_fileconv(const char* format, bool to_file, int comps, bool dev) {
+    if (!format) { set_error("fileconv: format is NULL"); return nullptr; }
+    for (const FmtInfo& f : FORMATS)
+        if (std::strcmp(f.name, format) == 0) {
+            Block* b = new (std::nothrow) FileConvBlock(f, to_file, comps, dev);
+            if (!b) set_error("out of memory");
+            return b;
+        }
+    set_error("Unsupported format (\"%s\")", format);
     return nullptr;
 }
 

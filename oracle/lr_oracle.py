@@ -567,3 +567,39 @@ def iq_file_convert(raw, fmt):
     v = np.frombuffer(np.asarray(raw, dtype=np.uint8).tobytes(), dtype=np.dtype(dt)).astype(np.float64)
     y = ((v - offset) / scale).astype(F32)
     return (y[0::2] + 1j * y[1::2]).astype(C64)
+
+
+def real_file_convert(raw, fmt):
+    """radio/blocks/sources/realfile.lua:86-104: real samples of `fmt` -> float32 (same map as iq_file_convert)."""
+    dt, offset, scale = IQ_FORMATS[fmt]
+    v = np.frombuffer(np.asarray(raw, dtype=np.uint8).tobytes(), dtype=np.dtype(dt)).astype(np.float64)
+    return ((v - offset) / scale).astype(F32)
+
+
+def file_sink_convert(x, fmt):
+    """IQFileSink:process (radio/blocks/sinks/iqfile.lua:66-80), RealFileSink / WAVFileSink:process
+    (sinks/wavfile.lua:170-186): raw = x*scale + offset in double, stored into the C integer type (truncation toward
+    zero; float formats: rounding to float32 / exact float64), in the file's byte order.  Complex input is written as
+    interleaved I/Q.  Returns the file bytes (uint8).  Values outside [-1, 1] saturate (undefined in the reference)."""
+    dt, offset, scale = IQ_FORMATS[fmt]
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        x = np.stack([x.real, x.imag], axis=1).reshape(-1)
+    v = x.astype(F32).astype(np.float64) * scale + offset
+    dt = np.dtype(dt)
+    if dt.kind == "f":
+        out = v.astype(dt)
+    else:
+        info = np.iinfo(dt)
+        out = np.clip(np.trunc(v), info.min, info.max).astype(np.int64).astype(dt)
+    return np.frombuffer(out.tobytes(), dtype=np.uint8).copy()
+
+
+def wav_header(num_samples, num_channels, bits_per_sample, rate):
+    """WAVFileSink headers (radio/blocks/sinks/wavfile.lua:135-160, sizes filled in by cleanup()): RIFF/WAVE, PCM
+    'fmt ' chunk of 16 bytes, 'data' chunk; all little endian."""
+    import struct
+    data = num_samples * num_channels * (bits_per_sample // 8)
+    return (b"RIFF" + struct.pack("<I", 36 + data) + b"WAVE" + b"fmt " +
+            struct.pack("<IHHIIHH", 16, 1, num_channels, int(rate), int(rate) * num_channels * (bits_per_sample // 8),
+                        num_channels * (bits_per_sample // 8), bits_per_sample) + b"data" + struct.pack("<I", data))

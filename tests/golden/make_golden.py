@@ -187,6 +187,18 @@ def main():
     np.savez_compressed(os.path.join(OUT, "iqfile_spec_raw.npz"), **arrays)
     print("iqfile_spec_raw: %d formats: %s" % (len(fmts), " ".join(fmts)))
 
+    # tests/blocks/sources/realfile_spec.gen.lua: same layout, one component per sample, Float32 outputs
+    s = open(os.path.join(REF, "tests", "blocks/sources/realfile_spec.gen.lua")).read()
+    arrays, fmts = {}, []
+    for i, m in enumerate(re.finditer(r'args = \{require\(\'tests\.buffer\'\)\.open\("([^"]*)"\), "(\w+)", 1\},\s*inputs = \{\},\s*outputs = \{', s)):
+        raw = bytes(int(h, 16) for h in re.findall(r"\\x([0-9a-f]{2})", m.group(1)))
+        arrays["v%d_raw" % i] = np.frombuffer(raw, dtype=np.uint8).copy()
+        arrays["v%d_out" % i] = LuaLit(s, m.end()).value()
+        fmts.append(m.group(2))
+    arrays["formats"] = np.array(fmts)
+    np.savez_compressed(os.path.join(OUT, "realfile_spec_raw.npz"), **arrays)
+    print("realfile_spec_raw: %d formats: %s" % (len(fmts), " ".join(fmts)))
+
     # tests/top_vectors.gen.lua: raw little-endian byte strings ("\x.."), tests/top_vectors.py:26-36
     s = open(os.path.join(REF, "tests", "top_vectors.gen.lua")).read()
     arrays = {}

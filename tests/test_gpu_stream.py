@@ -342,3 +342,27 @@ def test_long_fir_partitioned_overlap_save(M, kind):
     ref = scipy.signal.fftconvolve(x.astype(np.complex128), taps.astype(np.complex128))[:n].astype(np.complex64)
     close(got, ref)
     blk.cleanup()
+
+
+def test_wbfm_chain_u8_file_to_wav_file():
+    """u8 IQ file -> fused WBFM chain -> 16-bit WAV, both file formats converted inside the GPU flow graph (the H2D copy
+    carries 2 B/sample, the D2H copy 2 B/sample).  The PCM samples equal the oracle's within one LSB (a 1e-6 float
+    difference can cross a truncation boundary)."""
+    import io
+    n = 400000
+    x = O.synth_fm_iq(0, n)
+    u8 = np.clip(np.round(np.stack([x.real, x.imag], 1).reshape(-1) * 127.5 + 127.5), 0, 255).astype(np.uint8)
+    f = io.BytesIO()
+    src, snk = radio.IQFileSource(u8.tobytes(), "u8", 1102500.0, chunk=150001), radio.WAVFileSink(f, 1, 16)
+    top = radio.CompositeBlock()
+    top.connect(src, radio.TunerBlock(-250e3, 200e3, 5), radio.FrequencyDiscriminatorBlock(1.25),
+                radio.LowpassFilterBlock(128, 15e3), radio.FMDeemphasisFilterBlock(75e-6), radio.DownsamplerBlock(5), snk)
+    top.run(False)
+    desc = top.describe_gpu_graph()
+    assert desc.startswith("iqconv(u8) | tuner+discrim") and desc.endswith("realsink(s16le)"), desc
+    ref = O.wbfm_mono_chain().process(O.iq_file_convert(u8, "u8"))
+    wav = f.getvalue()
+    assert wav[:44] == O.wav_header(len(ref), 1, 16, 44100)
+    got = np.frombuffer(wav[44:], "<i2").astype(np.int64)
+    want = np.frombuffer(O.file_sink_convert(ref, "s16le").tobytes(), "<i2").astype(np.int64)
+    assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1

@@ -112,3 +112,42 @@ def test_oracle_iq_file_formats():
     for i, fmt in enumerate(z["formats"]):
         ok, msg = epsilon_ok(O.iq_file_convert(z["v%d_raw" % i], str(fmt)), z["v%d_out" % i], 1e-6)
         assert ok, "%s: %s" % (fmt, msg)
+
+
+def test_oracle_real_file_formats():
+    """tests/blocks/sources/realfile_spec.gen.lua: the 14 RealFileSource formats (raw bytes -> Float32), epsilon 1e-6."""
+    z = np.load(GOLDEN_DIR + "/realfile_spec_raw.npz")
+    assert len(z["formats"]) == 14
+    for i, fmt in enumerate(z["formats"]):
+        ok, msg = epsilon_ok(O.real_file_convert(z["v%d_raw" % i], str(fmt)), z["v%d_out" % i], 1e-6)
+        assert ok, "%s: %s" % (fmt, msg)
+
+
+# WAV headers of the reference's sink spec (tests/blocks/sinks/wavfile_spec.lua:22-35): 256 samples per channel at 44100 Hz
+WAV_HEADERS = {
+    (8, 1): "524946462401000057415645666d74201000000001000100 44ac0000 44ac0000 0100 0800 64617461 00010000",
+    (8, 2): "524946462402000057415645666d74201000000001000200 44ac0000 88580100 0200 0800 64617461 00020000",
+    (16, 1): "524946462402000057415645666d74201000000001000100 44ac0000 88580100 0200 1000 64617461 00020000",
+    (16, 2): "524946462404000057415645666d74201000000001000200 44ac0000 10b10200 0400 1000 64617461 00040000",
+    (32, 1): "524946462404000057415645666d74201000000001000100 44ac0000 10b10200 0400 2000 64617461 00040000",
+    (32, 2): "524946462408000057415645666d74201000000001000200 44ac0000 20620500 0800 2000 64617461 00080000",
+}
+
+
+def test_oracle_file_sinks_round_trip_and_wav_header():
+    """tests/blocks/sinks/{iqfile,realfile,wavfile}_spec.lua write random samples and read them back within a per-format
+    epsilon (1e-2 for 8 bit, 1e-4 for 16 bit, 1e-6 otherwise); the WAV headers are the spec's golden bytes."""
+    rng = np.random.default_rng(5)
+    xr = rng.uniform(-1, 1, 1000).astype(np.float32)
+    xc = (rng.uniform(-1, 1, 1000) + 1j * rng.uniform(-1, 1, 1000)).astype(np.complex64)
+    for fmt in O.IQ_FORMATS:
+        eps = 1e-2 if "8" in fmt and "f" not in fmt else (1e-4 if "16" in fmt else 1e-6)
+        back = O.real_file_convert(O.file_sink_convert(xr, fmt), fmt)
+        assert np.max(np.abs(back - xr)) <= eps, fmt
+        back = O.iq_file_convert(O.file_sink_convert(xc, fmt), fmt)
+        assert np.max(np.abs(back - xc)) <= eps * 1.5, fmt
+    # truncation toward zero, end points
+    assert list(O.file_sink_convert(np.array([-1.0, -0.004, 0.0, 0.004, 1.0], np.float32), "u8")) == [0, 126, 127, 128, 255]
+    assert list(O.file_sink_convert(np.array([-1.0, 1.0], np.float32), "s16le").view("<i2")) == [-32767, 32767]
+    for (bits, ch), hexs in WAV_HEADERS.items():
+        assert O.wav_header(256, ch, bits, 44100) == bytes.fromhex(hexs.replace(" ", "")), (bits, ch)
