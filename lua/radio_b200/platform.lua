@@ -40,6 +40,10 @@ lrb200_block_t *lrb200_iir_create_rrrf(const float32_t *b, unsigned int nb, cons
 lrb200_block_t *lrb200_iir_create_crcf(const float32_t *b, unsigned int nb, const float32_t *a, unsigned int na, unsigned int flags);
 lrb200_block_t *lrb200_cmag_create(unsigned int flags);
 lrb200_block_t *lrb200_c2r_create(unsigned int flags);
+lrb200_block_t *lrb200_iqconv_create(const char *format, unsigned int flags);
+lrb200_block_t *lrb200_realconv_create(const char *format, unsigned int flags);
+lrb200_block_t *lrb200_iqsink_create(const char *format, unsigned int flags);
+lrb200_block_t *lrb200_realsink_create(const char *format, unsigned int flags);
 
 lrb200_graph_t *lrb200_graph_create(void);
 int lrb200_graph_append(lrb200_graph_t *g, lrb200_block_t *q);
