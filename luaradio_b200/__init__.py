@@ -14,7 +14,7 @@ All arithmetic runs in libluaradio_b200.so (hand-written CUDA, include/lrb200.h)
 """
 from . import _lib, block, types
 from .block import Block, Input, Output, factory
-from .composite import (ArraySink, ArraySource, CompositeBlock, DecimatorBlock, IQFileSink, IQFileSource, RawFileSink,
+from .composite import (AMEnvelopeDemodulator, NBFMDemodulator, SSBDemodulator, ArraySink, ArraySource, CompositeBlock, DecimatorBlock, IQFileSink, IQFileSource, RawFileSink,
                         RawFileSource, RealFileSink, RealFileSource, TunerBlock, WAVFileSink, WBFMMonoDemodulator)
 from .signal_blocks import (BandpassFilterBlock, BandstopFilterBlock, ComplexBandpassFilterBlock,
                             ComplexBandstopFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,

@@ -15,7 +15,8 @@ import numpy as np
 
 from . import _lib
 from .block import Block, Input, Output, Pipe, Port
-from .signal_blocks import (DownsamplerBlock, FMDeemphasisFilterBlock, FrequencyDiscriminatorBlock,
+from .signal_blocks import (ComplexBandpassFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,
+                            SinglepoleHighpassFilterBlock, DownsamplerBlock, FMDeemphasisFilterBlock, FrequencyDiscriminatorBlock,
                             FrequencyTranslatorBlock, GPUBlock, LowpassFilterBlock)
 from .types import ComplexFloat32, Float32, Vector
 
@@ -628,3 +629,55 @@ class WBFMMonoDemodulator(CompositeBlock):
         self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
         self.connect(self, "in", fm_demod, "in")
         self.connect(self, "out", af_deemphasis, "out")
+
+
+class NBFMDemodulator(CompositeBlock):
+    """composites/nbfmdemodulator.lua:26-41: Lowpass(128, deviation + bandwidth) -> FrequencyDiscriminator(deviation /
+    bandwidth) -> Lowpass(128, bandwidth).  Three GPU blocks -> one flow graph (FFT FIR | discriminator | FFT FIR)."""
+    name = "NBFMDemodulator"
+
+    def instantiate(self, deviation=None, bandwidth=None):
+        CompositeBlock.instantiate(self)
+        deviation = deviation or 5e3
+        bandwidth = bandwidth or 4e3
+        rf_filter = LowpassFilterBlock(128, 2 * (deviation + bandwidth) / 2)
+        fm_demod = FrequencyDiscriminatorBlock(deviation / bandwidth)
+        af_filter = LowpassFilterBlock(128, bandwidth)
+        self.connect(rf_filter, fm_demod, af_filter)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
+        self.connect(self, "in", rf_filter, "in")
+        self.connect(self, "out", af_filter, "out")
+
+
+class AMEnvelopeDemodulator(CompositeBlock):
+    """composites/amenvelopedemodulator.lua:24-38: ComplexMagnitude -> SinglepoleHighpass(100) -> Lowpass(128, bandwidth)."""
+    name = "AMEnvelopeDemodulator"
+
+    def instantiate(self, bandwidth=None):
+        CompositeBlock.instantiate(self)
+        bandwidth = bandwidth or 5e3
+        am_demod = ComplexMagnitudeBlock()
+        dcr_filter = SinglepoleHighpassFilterBlock(100)
+        af_filter = LowpassFilterBlock(128, bandwidth)
+        self.connect(am_demod, dcr_filter, af_filter)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
+        self.connect(self, "in", am_demod, "in")
+        self.connect(self, "out", af_filter, "out")
+
+
+class SSBDemodulator(CompositeBlock):
+    """composites/ssbdemodulator.lua:25-43: ComplexBandpass(129, {0, +-bandwidth}) -> ComplexToReal -> Lowpass(128, bandwidth)."""
+    name = "SSBDemodulator"
+
+    def instantiate(self, sideband, bandwidth=None):
+        CompositeBlock.instantiate(self)
+        assert sideband, "Missing argument #1 (sideband)"
+        assert sideband in ("lsb", "usb"), "Sideband should be 'lsb' or 'usb'"
+        bandwidth = bandwidth or 3e3
+        sb_filter = ComplexBandpassFilterBlock(129, [0, -bandwidth] if sideband == "lsb" else [0, bandwidth])
+        am_demod = ComplexToRealBlock()
+        af_filter = LowpassFilterBlock(128, bandwidth)
+        self.connect(sb_filter, am_demod, af_filter)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
+        self.connect(self, "in", sb_filter, "in")
+        self.connect(self, "out", af_filter, "out")

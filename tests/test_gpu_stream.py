@@ -366,3 +366,44 @@ def test_wbfm_chain_u8_file_to_wav_file():
     got = np.frombuffer(wav[44:], "<i2").astype(np.int64)
     want = np.frombuffer(O.file_sink_convert(ref, "s16le").tobytes(), "<i2").astype(np.int64)
     assert got.shape == want.shape and np.max(np.abs(got - want)) <= 1
+
+
+def run_demod(demod, x, rate, chunk):
+    src, snk = radio.ArraySource(x, rate, chunk), radio.ArraySink()
+    top = radio.CompositeBlock()
+    top.connect(src, demod, snk)
+    top.run(False)
+    return snk.result(), top
+
+
+@pytest.mark.parametrize("chunk", [1 << 20, 33333])
+def test_nbfm_am_ssb_demodulators(chunk):
+    """composites/nbfmdemodulator.lua, amenvelopedemodulator.lua, ssbdemodulator.lua (the chains that
+    need no new block): each composite runs as one GPU flow graph and equals the oracle chain of the same blocks."""
+    n, rate = 400000, 48000.0
+    # NBFM: 5 kHz deviation FM at baseband with a little noise
+    x = O.synth_fm_iq(0, n, 1, rate, 0.0, 5e3, 0.7, 0.005)
+    got, top = run_demod(radio.NBFMDemodulator(), x, rate, chunk)
+    ref = O.Chain(O.lowpass_filter(128, 9e3, rate, True), O.FrequencyDiscriminator(5e3 / 4e3),
+                  O.lowpass_filter(128, 4e3, rate, False)).process(x)
+    close(got, ref)
+    assert np.max(np.abs(ref[1000:])) > 0.05
+    assert top.describe_gpu_graph().count("|") == 2
+    # AM envelope: carrier with 60 % modulation by two tones, plus noise
+    t = np.arange(n) / rate
+    env = 0.5 * (1 + 0.3 * np.sin(2 * np.pi * 440 * t) + 0.3 * np.sin(2 * np.pi * 1250 * t))
+    rng = np.random.default_rng(3)
+    xa = (env * np.exp(2j * np.pi * 0.013 * np.arange(n)) + 0.003 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    got, top = run_demod(radio.AMEnvelopeDemodulator(), xa, rate, chunk)
+    b, a = O.singlepole_highpass_taps(100, rate)
+    ref = O.Chain(O.complex_magnitude, O.IIRFilterFast(b, a, False), O.lowpass_filter(128, 5e3, rate, False)).process(xa)
+    close(got, ref)
+    assert np.max(np.abs(ref[20000:])) > 0.1
+    # SSB, both sidebands
+    xs = (rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)).astype(np.complex64)
+    for sb, cut in (("usb", [0, 3e3]), ("lsb", [0, -3e3])):
+        got, top = run_demod(radio.SSBDemodulator(sb), xs, rate, chunk)
+        ref = O.Chain(O.complex_bandpass_filter(129, cut, rate), O.complex_to_real, O.lowpass_filter(128, 3e3, rate, False)).process(xs)
+        close(got, ref)
+    with pytest.raises(AssertionError):
+        radio.SSBDemodulator("dsb")
