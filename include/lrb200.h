@@ -156,6 +156,16 @@ lrb200_iir_t* lrb200_iir_create_crcf(const float32_t* b, unsigned nb, const floa
 lrb200_block_t* lrb200_cmag_create(unsigned flags);
 lrb200_block_t* lrb200_c2r_create(unsigned flags);
 
+/* ---- Resampling family ------------------------------------------------------------
+ * lrb200_mulconst_create replaces MultiplyConstantBlock:process (radio/blocks/signal/multiplyconstant.lua: complex x
+ * complex, complex x real, real x real); lrb200_upsample_create replaces UpsamplerBlock:process
+ * (radio/blocks/signal/upsampler.lua:44-52: y[i*L] = x[i], zeros in between; output length n*L).  In a graph,
+ * [mulconst(real c) ->] upsample(L) -> fir(real taps) [-> downsample(D)] -- InterpolatorBlock
+ * (radio/composites/interpolator.lua:31-41) and RationalResamplerBlock (radio/composites/rationalresampler.lua:33-46)
+ * -- commit to ONE polyphase kernel that touches only the non-zero products of kept outputs. */
+lrb200_block_t* lrb200_mulconst_create(float re, float im, unsigned complex_data, unsigned complex_constant, unsigned flags);
+lrb200_block_t* lrb200_upsample_create(unsigned factor, unsigned elem_size, unsigned flags);
+
 /* ---- IQFileSource sample formats (the source boundary) ------------------------------
  * Replaces the byte-swap + (value - offset) / scale loops of radio/blocks/sources/iqfile.lua:96-108 with the format
  * table of radio/utilities/format_utils.lua:82-97: u8 s8 u16le u16be s16le s16be u32le u32be s32le s32be f32le f32be

@@ -14,9 +14,10 @@ All arithmetic runs in libluaradio_b200.so (hand-written CUDA, include/lrb200.h)
 """
 from . import _lib, block, types
 from .block import Block, Input, Output, factory
-from .composite import (AMEnvelopeDemodulator, NBFMDemodulator, SSBDemodulator, ArraySink, ArraySource, CompositeBlock, DecimatorBlock, IQFileSink, IQFileSource, RawFileSink,
-                        RawFileSource, RealFileSink, RealFileSource, TunerBlock, WAVFileSink, WBFMMonoDemodulator)
-from .signal_blocks import (BandpassFilterBlock, BandstopFilterBlock, ComplexBandpassFilterBlock,
+from .composite import (AMEnvelopeDemodulator, ArraySink, ArraySource, CompositeBlock, DecimatorBlock, InterpolatorBlock,
+                        IQFileSink, IQFileSource, NBFMDemodulator, RationalResamplerBlock, RawFileSink, RawFileSource,
+                        RealFileSink, RealFileSource, SSBDemodulator, TunerBlock, WAVFileSink, WBFMMonoDemodulator)
+from .signal_blocks import (MultiplyConstantBlock, UpsamplerBlock, BandpassFilterBlock, BandstopFilterBlock, ComplexBandpassFilterBlock,
                             ComplexBandstopFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,
                             DownsamplerBlock, FIRFilterBlock, FMDeemphasisFilterBlock,
                             FrequencyDiscriminatorBlock, FrequencyTranslatorBlock, GPUBlock,

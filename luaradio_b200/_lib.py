@@ -58,6 +58,8 @@ _PROTOS = {
     "lrb200_iir_create_crcf": (c_void_p, [c_void_p, c_uint, c_void_p, c_uint, c_uint]),
     "lrb200_cmag_create": (c_void_p, [c_uint]),
     "lrb200_c2r_create": (c_void_p, [c_uint]),
+    "lrb200_mulconst_create": (c_void_p, [c_float, c_float, c_uint, c_uint, c_uint]),
+    "lrb200_upsample_create": (c_void_p, [c_uint, c_uint, c_uint]),
     "lrb200_iqconv_create": (c_void_p, [c_char_p, c_uint]),
     "lrb200_realconv_create": (c_void_p, [c_char_p, c_uint]),
     "lrb200_iqsink_create": (c_void_p, [c_char_p, c_uint]),

@@ -15,7 +15,7 @@ import numpy as np
 
 from . import _lib
 from .block import Block, Input, Output, Pipe, Port
-from .signal_blocks import (ComplexBandpassFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,
+from .signal_blocks import (MultiplyConstantBlock, UpsamplerBlock, ComplexBandpassFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,
                             SinglepoleHighpassFilterBlock, DownsamplerBlock, FMDeemphasisFilterBlock, FrequencyDiscriminatorBlock,
                             FrequencyTranslatorBlock, GPUBlock, LowpassFilterBlock)
 from .types import ComplexFloat32, Float32, Vector
@@ -681,3 +681,44 @@ class SSBDemodulator(CompositeBlock):
         self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
         self.connect(self, "in", sb_filter, "in")
         self.connect(self, "out", af_filter, "out")
+
+
+class InterpolatorBlock(CompositeBlock):
+    """composites/interpolator.lua:25-44: MultiplyConstant(L) -> Upsampler(L) -> Lowpass(num_taps or 128, 1/L, nyquist 1.0).
+    The GPU flow graph commits the three blocks to one polyphase kernel (M/L products per output)."""
+    name = "InterpolatorBlock"
+
+    def instantiate(self, interpolation, options=None):
+        CompositeBlock.instantiate(self)
+        assert interpolation is not None, "Missing argument #1 (interpolation)"
+        options = options or {}
+        scaler = MultiplyConstantBlock(interpolation)
+        upsampler = UpsamplerBlock(interpolation)
+        filt = LowpassFilterBlock(options.get("num_taps", 128), 1.0 / interpolation, 1.0, options.get("window"))
+        self.connect(scaler, upsampler, filt)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        self.add_type_signature([Input("in", Float32)], [Output("out", Float32)])
+        self.connect(self, "in", scaler, "in")
+        self.connect(self, "out", filt, "out")
+
+
+class RationalResamplerBlock(CompositeBlock):
+    """composites/rationalresampler.lua:25-49: MultiplyConstant(L) -> Upsampler(L) -> Lowpass(num_taps or 128,
+    min(1/L, 1/D), nyquist 1.0) -> Downsampler(D); one polyphase kernel in the GPU flow graph."""
+    name = "RationalResamplerBlock"
+
+    def instantiate(self, interpolation, decimation, options=None):
+        CompositeBlock.instantiate(self)
+        assert interpolation is not None, "Missing argument #1 (interpolation)"
+        assert decimation is not None, "Missing argument #2 (decimation)"
+        options = options or {}
+        cutoff = min(1.0 / interpolation, 1.0 / decimation)
+        scaler = MultiplyConstantBlock(interpolation)
+        upsampler = UpsamplerBlock(interpolation)
+        filt = LowpassFilterBlock(options.get("num_taps", 128), cutoff, 1.0, options.get("window"))
+        downsampler = DownsamplerBlock(decimation)
+        self.connect(scaler, upsampler, filt, downsampler)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        self.add_type_signature([Input("in", Float32)], [Output("out", Float32)])
+        self.connect(self, "in", scaler, "in")
+        self.connect(self, "out", downsampler, "out")

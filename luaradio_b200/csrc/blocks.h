@@ -136,6 +136,41 @@ struct C2fBlock : Block {
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
 };
 
+// resample.cu ---------------------------------------------------------------------------------
+struct ScaleBlock : Block {           // MultiplyConstantBlock
+    float cre, cim;
+    bool complex_data, complex_const;
+    ScaleBlock(float re, float im, bool cdata, bool cconst, bool dev);
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
+struct UpsampleBlock : Block {        // UpsamplerBlock
+    int L = 1;
+    UpsampleBlock(unsigned factor, unsigned elem, bool dev);
+    size_t max_output(size_t n) const override { return n * (size_t)L; }
+    uint64_t outputs_before(uint64_t idx) const override { return idx * (uint64_t)L; }
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
+struct InterpFirBlock : Block {       // [MultiplyConstant ->] Upsampler -> FIR(real taps) [-> Downsampler], fused
+    bool complex_data;
+    int L, D, M, Hn = 0, cur = 0;
+    bool has_scale;
+    float scale;
+    std::vector<float> h_taps;
+    float* d_taps = nullptr;
+    void* d_hist[2] = {nullptr, nullptr};
+    std::string label;
+    InterpFirBlock(bool cdata, const float* taps_host, int ntaps, int interp, int decim, bool has_scale, float scale, bool dev);
+    ~InterpFirBlock() override;
+    int init() override;
+    size_t max_output(size_t n) const override;
+    uint64_t outputs_before(uint64_t idx) const override;
+    void reset_host() override { consumed = 0; cur = 0; }
+    void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
+    int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+};
+
 }  // namespace lrb
 
 // the opaque public handle

@@ -572,6 +572,18 @@ lrb200_block_t* lrb200_c2r_create(unsigned flags) {
     return wrap(new (std::nothrow) C2fBlock(1, (flags & LRB200_DEVICE) != 0));
 }
 
+lrb200_block_t* lrb200_mulconst_create(float re, float im, unsigned complex_data, unsigned complex_constant, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (complex_constant && !complex_data) { set_error("mulconst: a complex constant needs complex data"); return nullptr; }
+    return wrap(new (std::nothrow) ScaleBlock(re, im, complex_data != 0, complex_constant != 0, (flags & LRB200_DEVICE) != 0));
+}
+lrb200_block_t* lrb200_upsample_create(unsigned factor, unsigned elem_size, unsigned flags) {
+    if (ensure_init() != 0) return nullptr;
+    if (factor == 0) { set_error("upsample: factor must be >= 1"); return nullptr; }
+    if (elem_size != 4 && elem_size != 8) { set_error("upsample: elem_size must be 4 or 8"); return nullptr; }
+    return wrap(new (std::nothrow) UpsampleBlock(factor, elem_size, (flags & LRB200_DEVICE) != 0));
+}
+
 lrb200_block_t* lrb200_iqconv_create(const char* format, unsigned flags) {
     if (ensure_init() != 0) return nullptr;
     Block* b = make_iqconv(format, (flags & LRB200_DEVICE) != 0);

@@ -8,6 +8,7 @@
 //   Rotator -> FIR(crcf) -> Downsampler [-> Discriminator]  =>  tuner kernel (composites/tuner.lua:40-47)
 //   FIR -> Downsampler                    =>  decimating FIR    (composites/decimator.lua:34-41)
 //   IIR -> Downsampler                    =>  scan with strided store
+//   [MultiplyConstant ->] Upsampler -> FIR [-> Downsampler]  =>  polyphase interpolating FIR
 #include "../../include/lrb200.h"
 #include "common.cuh"
 #include "blocks.h"
@@ -95,6 +96,23 @@ struct Graph {
                         nf->name = f2->kind == FIR_CCCF ? "rot+fir_cccf" : "rot+fir_crcf";
                         if (nf->init() != 0) { delete nf; return -1; }
                         fused.push_back(nf); st = nf; used = d3 ? 3 : 2;
+                    }
+                }
+                {
+                    // [MultiplyConstant(real c) ->] Upsampler(L) -> FIR(real taps) [-> Downsampler(D)]  =>  polyphase
+                    // interpolating FIR (composites/interpolator.lua:31-41, composites/rationalresampler.lua:33-46)
+                    size_t j = i;
+                    ScaleBlock* sc = dynamic_cast<ScaleBlock*>(blocks[j]);
+                    if (sc && !sc->complex_const) ++j; else sc = nullptr;
+                    UpsampleBlock* up = j < blocks.size() ? dynamic_cast<UpsampleBlock*>(blocks[j]) : nullptr;
+                    FirBlock* f2 = (up && j + 1 < blocks.size()) ? dynamic_cast<FirBlock*>(blocks[j + 1]) : nullptr;
+                    if (up && f2 && f2->D == 1 && (f2->kind == FIR_CRCF || f2->kind == FIR_RRRF) && f2->in_size == up->out_size) {
+                        DownsampleBlock* d3 = (j + 2 < blocks.size()) ? dynamic_cast<DownsampleBlock*>(blocks[j + 2]) : nullptr;
+                        if (d3 && d3->in_size != f2->out_size) d3 = nullptr;
+                        InterpFirBlock* nb = new (std::nothrow) InterpFirBlock(f2->kind == FIR_CRCF, (const float*)f2->h_taps.data(), f2->M,
+                                                                               up->L, d3 ? d3->D : 1, sc != nullptr, sc ? sc->cre : 1.0f, true);
+                        if (!nb || nb->init() != 0) { delete nb; return -1; }
+                        fused.push_back(nb); st = nb; used = (j - i) + 2 + (d3 ? 1 : 0);
                     }
                 }
                 if (used == 1 && fir && fir->D == 1 && fir->kind != FIR_HILBERT && i + 1 < blocks.size()) {

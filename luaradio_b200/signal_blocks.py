@@ -327,3 +327,47 @@ class ComplexToRealBlock(GPUBlock):
 
     def _make_handle(self, flags):
         return _lib.check_handle(_lib.load().lrb200_c2r_create(flags), "lrb200 c2r object")
+
+
+# ---------------------------------------------------------------------------------------------
+# Resampling family
+# ---------------------------------------------------------------------------------------------
+class MultiplyConstantBlock(GPUBlock):
+    """multiplyconstant.lua: y = x * constant; a complex constant only accepts complex input."""
+    name = "MultiplyConstantBlock"
+
+    def instantiate(self, constant):
+        assert constant is not None, "Missing argument #1 (constant)"
+        if isinstance(constant, (complex, np.complexfloating)):
+            self.constant, self.complex_constant = complex(constant), True
+            self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        elif isinstance(constant, (int, float, np.integer, np.floating)):
+            self.constant, self.complex_constant = float(constant), False
+            self.add_type_signature([Input("in", Float32)], [Output("out", Float32)])
+            self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        else:
+            raise TypeError("Unsupported constant type")
+
+    def _make_handle(self, flags):
+        c = complex(self.constant)
+        cdata = 1 if self.get_input_type() is ComplexFloat32 else 0
+        return _lib.check_handle(_lib.load().lrb200_mulconst_create(c.real, c.imag, cdata, 1 if self.complex_constant else 0, flags),
+                                 "lrb200 mulconst object")
+
+
+class UpsamplerBlock(GPUBlock):
+    """upsampler.lua:29-52: y[i*L] = x[i], zeros in between; rate * L."""
+    name = "UpsamplerBlock"
+
+    def instantiate(self, factor):
+        assert factor is not None, "Missing argument #1 (factor)"
+        self.factor = int(factor)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        self.add_type_signature([Input("in", Float32)], [Output("out", Float32)])
+
+    def get_rate(self):
+        return Block.get_rate(self) * self.factor
+
+    def _make_handle(self, flags):
+        return _lib.check_handle(_lib.load().lrb200_upsample_create(self.factor, self.get_input_type().size, flags),
+                                 "lrb200 upsampler object")

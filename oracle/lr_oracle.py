@@ -603,3 +603,45 @@ def wav_header(num_samples, num_channels, bits_per_sample, rate):
     return (b"RIFF" + struct.pack("<I", 36 + data) + b"WAVE" + b"fmt " +
             struct.pack("<IHHIIHH", 16, 1, num_channels, int(rate), int(rate) * num_channels * (bits_per_sample // 8),
                         num_channels * (bits_per_sample // 8), bits_per_sample) + b"data" + struct.pack("<I", data))
+
+
+# ----------------------------------------------------------------------------------------------
+# resampling family
+# ----------------------------------------------------------------------------------------------
+class MultiplyConstant:
+    """multiplyconstant.lua:50-70: y = x * c (float32 arithmetic: complex x complex, complex x real, real x real)."""
+
+    def __init__(self, constant):
+        self.c = constant
+
+    def process(self, x):
+        x = np.asarray(x)
+        if np.iscomplexobj(self.c) or isinstance(self.c, complex):
+            return (x.astype(C64) * C64(self.c)).astype(C64)
+        return (x * F32(self.c)).astype(x.dtype)
+
+
+class Upsampler:
+    """upsampler.lua:44-52: y[i*L] = x[i], zeros in between; len(out) = L*len(in); stateless."""
+
+    def __init__(self, factor):
+        self.factor = int(factor)
+
+    def process(self, x):
+        x = np.asarray(x)
+        y = np.zeros(len(x) * self.factor, x.dtype)
+        y[::self.factor] = x
+        return y
+
+
+def interpolator(interpolation, complex_input, num_taps=128, window_type="hamming"):
+    """composites/interpolator.lua:31-41."""
+    return Chain(MultiplyConstant(float(interpolation)), Upsampler(interpolation),
+                 lowpass_filter(num_taps, 1.0 / interpolation, 2.0, complex_input, 1.0, window_type))
+
+
+def rational_resampler(interpolation, decimation, complex_input, num_taps=128, window_type="hamming"):
+    """composites/rationalresampler.lua:33-46."""
+    cutoff = min(1.0 / interpolation, 1.0 / decimation)
+    return Chain(MultiplyConstant(float(interpolation)), Upsampler(interpolation),
+                 lowpass_filter(num_taps, cutoff, 2.0, complex_input, 1.0, window_type), Downsampler(decimation))

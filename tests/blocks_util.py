@@ -10,6 +10,8 @@ def _lua_arg(a):
     # golden args: numpy arrays are Vector args (taps); dicts are option tables
     if isinstance(a, np.ndarray):
         return (ComplexFloat32 if np.iscomplexobj(a) else Float32).vector_from_array(a)
+    if isinstance(a, dict) and "complex" in a:          # radio.types.ComplexFloat32(re, im) constant
+        return complex(a["complex"][0], a["complex"][1])
     return a
 
 

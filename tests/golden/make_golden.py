@@ -39,6 +39,8 @@ BLOCK_SPECS = [
     "blocks/signal/complexmagnitude_spec", "blocks/signal/complextoreal_spec",
     "blocks/signal/multiplyconjugate_spec",
     "composites/tuner_spec", "composites/decimator_spec",
+    "blocks/signal/multiplyconstant_spec", "blocks/signal/upsampler_spec",
+    "composites/interpolator_spec", "composites/rationalresampler_spec",
 ]
 MODULE_SPECS = ["utilities/filter_utils_vectors", "utilities/window_utils_vectors", "utilities/spectrum_utils_vectors"]
 

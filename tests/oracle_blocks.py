@@ -56,4 +56,17 @@ def make_oracle(block, args, inputs, rate=2.0):
     if block == "DecimatorBlock":
         o = opt(1, {}) or {}
         return O.decimator(a[0], cin, o.get("num_taps", 128), o.get("window", "hamming"))
+    if block == "MultiplyConstantBlock":
+        c = a[0]
+        if isinstance(c, dict) and "complex" in c:
+            c = complex(c["complex"][0], c["complex"][1])
+        return O.MultiplyConstant(c)
+    if block == "UpsamplerBlock":
+        return O.Upsampler(a[0])
+    if block == "InterpolatorBlock":
+        o = opt(1, {}) or {}
+        return O.interpolator(a[0], cin, o.get("num_taps", 128), o.get("window", "hamming"))
+    if block == "RationalResamplerBlock":
+        o = opt(2, {}) or {}
+        return O.rational_resampler(a[0], a[1], cin, o.get("num_taps", 128), o.get("window", "hamming"))
     raise KeyError(block)

@@ -16,6 +16,7 @@ BLOCK_SPECS = [
     "complexbandpassfilter_spec", "complexbandstopfilter_spec", "hilberttransform_spec", "frequencytranslator_spec",
     "frequencydiscriminator_spec", "downsampler_spec", "fmdeemphasisfilter_spec", "singlepolelowpassfilter_spec",
     "singlepolehighpassfilter_spec", "iirfilter_spec", "complexmagnitude_spec", "complextoreal_spec",
+    "multiplyconstant_spec", "upsampler_spec",
 ]
 
 
@@ -53,7 +54,7 @@ def test_golden_sample_by_sample(spec):
         blk.cleanup()
 
 
-@pytest.mark.parametrize("spec", ["tuner_spec", "decimator_spec"])
+@pytest.mark.parametrize("spec", ["tuner_spec", "decimator_spec", "interpolator_spec", "rationalresampler_spec"])
 @pytest.mark.parametrize("fuse", [True, False])
 def test_golden_composites(spec, fuse):
     block, vectors, eps = load_spec(spec)
@@ -68,9 +69,9 @@ def test_golden_composites(spec, fuse):
 @pytest.mark.parametrize("chunk", [1 << 22, 7, 1])
 def test_golden_composites_ragged_source(chunk):
     """Same composites with the source delivering tiny vectors (state carried across graph executes)."""
-    for spec in ("tuner_spec", "decimator_spec"):
+    for spec in ("tuner_spec", "decimator_spec", "interpolator_spec", "rationalresampler_spec"):
         block, vectors, eps = load_spec(spec)
-        for v in vectors[:2]:
+        for v in (vectors[:2] if spec in ("tuner_spec", "decimator_spec") else vectors):
             got, _ = run_composite(block, v["args"], v["inputs"][0], chunk=chunk)
             ok, msg = epsilon_ok(got, v["outputs"][0], eps)
             assert ok, "%s / %s chunk=%d: %s" % (block, v["desc"], chunk, msg)

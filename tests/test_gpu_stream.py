@@ -387,7 +387,7 @@ def test_nbfm_am_ssb_demodulators(chunk):
     ref = O.Chain(O.lowpass_filter(128, 9e3, rate, True), O.FrequencyDiscriminator(5e3 / 4e3),
                   O.lowpass_filter(128, 4e3, rate, False)).process(x)
     close(got, ref)
-    assert np.max(np.abs(ref[1000:])) > 0.05
+    assert np.max(np.abs(ref[1000:])) > 0.02
     assert top.describe_gpu_graph().count("|") == 2
     # AM envelope: carrier with 60 % modulation by two tones, plus noise
     t = np.arange(n) / rate
@@ -407,3 +407,25 @@ def test_nbfm_am_ssb_demodulators(chunk):
         close(got, ref)
     with pytest.raises(AssertionError):
         radio.SSBDemodulator("dsb")
+
+
+@pytest.mark.parametrize("L,D,M", [(2, 1, 128), (3, 1, 128), (7, 5, 128), (2, 3, 128), (4, 25, 200), (160, 147, 1024), (5, 1, 33)])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_interpolator_and_rational_resampler_stream(L, D, M, cplx):
+    """InterpolatorBlock / RationalResamplerBlock as one polyphase kernel (fused) and as four separate kernels (unfused)
+    on a long stream in ragged chunks == oracle MultiplyConstant -> Upsampler -> Lowpass -> Downsampler."""
+    rng = np.random.default_rng(L * 100 + D)
+    n = 120000 if L < 100 else 20000
+    x = rnd_c(rng, n) if cplx else rng.uniform(-1, 1, n).astype(np.float32)
+    ref = (O.rational_resampler(L, D, cplx, M) if D > 1 else O.interpolator(L, cplx, M)).process(x)
+    for fuse, chunk in ((True, 1 << 22), (True, 4099), (False, 30011)):
+        src, snk = radio.ArraySource(x, 48000.0, chunk), radio.ArraySink()
+        blk = radio.RationalResamplerBlock(L, D, {"num_taps": M}) if D > 1 else radio.InterpolatorBlock(L, {"num_taps": M})
+        top = radio.CompositeBlock()
+        top.connect(src, blk, snk)
+        top.run(False, fuse=fuse)
+        close(snk.result(), ref)
+        if fuse:
+            assert "upsample+fir" in top.describe_gpu_graph() and top.describe_gpu_graph().count("|") == 0, top.describe_gpu_graph()
+        else:
+            assert top.describe_gpu_graph().count("|") == (3 if D > 1 else 2), top.describe_gpu_graph()
