@@ -81,6 +81,85 @@ interp_fir_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __rest
     }
 }
 
+// ---- Interpolator (D == 1, 2 <= L <= 8): register-tiled polyphase kernel.  A thread owns IT_R consecutive inputs and
+// all L phases (IT_R * L accumulators); per tap row t it needs x[i - t] for its IT_R inputs, a window that slides by one
+// sample per row, so one new shared-memory value per row feeds IT_R * L multiply-adds.  The window is held as two aligned
+// register chunks A = x[s0 - tb*R .. +R) and B = x[s0 - (tb+1)*R .. +R): every index below is a compile-time constant and
+// the chunk loads are 128-bit.  Taps sit in shared memory as [t][p] and are read as warp-wide broadcasts.
+constexpr int IT_R = 4;
+constexpr int IT_THREADS = 128;
+
+// 4 consecutive samples from a 16-byte aligned shared-memory position (index a multiple of 4)
+__device__ __forceinline__ void load_chunk4(const float2* p, float2 (&o)[4]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    o[0] = make_float2(a.x, a.y); o[1] = make_float2(a.z, a.w); o[2] = make_float2(b.x, b.y); o[3] = make_float2(b.z, b.w);
+}
+__device__ __forceinline__ void load_chunk4(const float* p, float (&o)[4]) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0];
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w;
+}
+constexpr int IT_TILE = IT_R * IT_THREADS;        // inputs per CTA tile
+
+template <typename T, int L, bool SCALE>
+__global__ void __launch_bounds__(IT_THREADS)
+interp_tiled_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __restrict__ y, const float* __restrict__ taps_tp,
+                    long long n, int Hn, int Tt, float c) {
+    extern __shared__ __align__(16) unsigned char it_smem[];
+    float* hs = reinterpret_cast<float*>(it_smem);                       // [Tt][L]
+    T* xs = reinterpret_cast<T*>(it_smem + (((size_t)Tt * L * sizeof(float) + 15) & ~(size_t)15));   // [Tt + IT_TILE], xs[Tt + j] = x[tile0 + j]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Tt * L; i += IT_THREADS) hs[i] = taps_tp[i];
+    const long long ntiles = (n + IT_TILE - 1) / IT_TILE;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long tile0 = tile * IT_TILE;
+        __syncthreads();                                                 // previous tile's reads are done (and hs is staged)
+        for (int j = tid; j < Tt + IT_TILE; j += IT_THREADS) {
+            const long long i = tile0 - Tt + j;
+            T v{};
+            if (i >= 0) { if (i < n) v = x[i]; }
+            else if (Hn + i >= 0) v = hist[Hn + i];
+            if constexpr (SCALE) v = scaled(v, c);
+            xs[j] = v;
+        }
+        __syncthreads();
+        const int s0 = Tt + tid * IT_R;                                  // smem position of this thread's first input
+        T acc[IT_R][L];
+#pragma unroll
+        for (int r = 0; r < IT_R; ++r)
+#pragma unroll
+            for (int p = 0; p < L; ++p) acc[r][p] = T{};
+        T A[IT_R], B[IT_R];
+        load_chunk4(xs + s0, A);
+#pragma unroll 1
+        for (int tb = 0; tb < Tt / IT_R; ++tb) {
+            load_chunk4(xs + s0 - (tb + 1) * IT_R, B);
+#pragma unroll
+            for (int sft = 0; sft < IT_R; ++sft) {
+                float h[L];
+#pragma unroll
+                for (int p = 0; p < L; ++p) h[p] = hs[(tb * IT_R + sft) * L + p];
+#pragma unroll
+                for (int r = 0; r < IT_R; ++r) {
+                    const T xv = (r - sft >= 0) ? A[(r - sft >= 0) ? r - sft : 0] : B[(r - sft < 0) ? IT_R + r - sft : 0];
+#pragma unroll
+                    for (int p = 0; p < L; ++p) acc[r][p] = fma_tap(acc[r][p], xv, h[p]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < IT_R; ++r) A[r] = B[r];
+        }
+        const long long i0 = tile0 + (long long)tid * IT_R;
+#pragma unroll
+        for (int r = 0; r < IT_R; ++r) {
+            if (i0 + r < n) {
+                T* yo = y + (i0 + r) * L;
+#pragma unroll
+                for (int p = 0; p < L; ++p) yo[p] = acc[r][p];
+            }
+        }
+    }
+}
+
 int grid_for(long long n) {
     long long b = (n + 255) / 256;
     const long long cap = (long long)ctx().sm_count * 16;
@@ -139,12 +218,21 @@ InterpFirBlock::InterpFirBlock(bool cdata, const float* taps_host, int ntaps, in
 }
 InterpFirBlock::~InterpFirBlock() {
     cudaFree(d_taps);
+    cudaFree(d_taps_tp);
     cudaFree(d_hist[0]);
     cudaFree(d_hist[1]);
 }
 int InterpFirBlock::init() {
     LRB_CHECK(cudaMalloc(&d_taps, sizeof(float) * (size_t)M));
     LRB_CHECK(cudaMemcpy(d_taps, h_taps.data(), sizeof(float) * (size_t)M, cudaMemcpyHostToDevice));
+    Tt = ((M + L - 1) / L + IT_R - 1) / IT_R * IT_R;
+    if (D == 1 && L >= 2 && L <= 8 && (size_t)Tt * L * sizeof(float) + (size_t)(Tt + IT_TILE) * in_size + 16 <= 48 * 1024) {
+        std::vector<float> tp((size_t)Tt * L, 0.0f);
+        for (int k = 0; k < M; ++k) tp[(size_t)(k / L) * L + (k % L)] = h_taps[k];
+        LRB_CHECK(cudaMalloc(&d_taps_tp, sizeof(float) * tp.size()));
+        LRB_CHECK(cudaMemcpy(d_taps_tp, tp.data(), sizeof(float) * tp.size(), cudaMemcpyHostToDevice));
+        if (Hn < Tt) Hn = Tt;                     // the tile staging reads Tt samples of history
+    }
     for (int i = 0; i < 2; ++i) {
         LRB_CHECK(cudaMalloc(&d_hist[i], in_size * (size_t)Hn));
         LRB_CHECK(cudaMemset(d_hist[i], 0, in_size * (size_t)Hn));
@@ -162,7 +250,28 @@ int InterpFirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaS
     const long long no = m_hi - m_lo;
     *n_out = (size_t)no;
     if (n == 0) return 0;
-    if (no > 0) {
+    if (no > 0 && D == 1 && L >= 2 && L <= 8 && d_taps_tp) {
+        const long long ntiles = ((long long)n + IT_TILE - 1) / IT_TILE;
+        const int g = (int)std::min<long long>(ntiles, (long long)ctx().sm_count * 8);
+        const size_t smem = (((size_t)Tt * L * sizeof(float) + 15) & ~(size_t)15) + (size_t)(Tt + IT_TILE) * in_size;
+#define LRB_IT2(T, LL, S) interp_tiled_kernel<T, LL, S><<<g, IT_THREADS, smem, s>>>((const T*)dx, (const T*)d_hist[cur], (T*)dy, d_taps_tp, (long long)n, Hn, Tt, scale)
+#define LRB_IT(LL) \
+        if (complex_data) { if (has_scale) LRB_IT2(float2, LL, true); else LRB_IT2(float2, LL, false); } \
+        else { if (has_scale) LRB_IT2(float, LL, true); else LRB_IT2(float, LL, false); }
+        switch (L) {
+            case 2: LRB_IT(2); break;
+            case 3: LRB_IT(3); break;
+            case 4: LRB_IT(4); break;
+            case 5: LRB_IT(5); break;
+            case 6: LRB_IT(6); break;
+            case 7: LRB_IT(7); break;
+            default: LRB_IT(8); break;
+        }
+#undef LRB_IT
+#undef LRB_IT2
+        count_launch();
+        LRB_CHECK(cudaGetLastError());
+    } else if (no > 0) {
         const int g = grid_for(no);
 #define LRB_IF(T, S) interp_fir_kernel<T, S><<<g, 256, 0, s>>>((const T*)dx, (const T*)d_hist[cur], (T*)dy, d_taps, no, m_lo, (long long)consumed, Hn, L, D, M, scale)
         if (complex_data) { if (has_scale) LRB_IF(float2, true); else LRB_IF(float2, false); }
