@@ -39,7 +39,6 @@ constexpr int FF_WARPS = 8;                       // warps (= concurrent FFT blo
 constexpr int FF_THREADS = FF_WARPS * 32;
 constexpr int FF_XSTRIDE = 33;                    // padded row stride of the transpose tile (float2 units)
 constexpr int FF_XCH = 32 * FF_XSTRIDE;           // float2 per warp-private tile
-constexpr size_t FF_SMEM = (size_t)(FF_N + FF_N + FF_WARPS * FF_XCH) * sizeof(float2);
 
 __device__ __forceinline__ float2 cmul_conj_if(float2 a, float2 w, bool conj) {
     // a * w  or  a * conj(w)
@@ -60,9 +59,6 @@ struct FftArgs {
     long long first;          // decimation: keep outputs at input index first + j*D
     uint64_t turns_fix, g0;   // fused translator
     int M, D;
-    int hist_len;             // samples in `hist` (total taps - 1; > M-1 for one partition of a long filter)
-    int in_shift;             // partitioned long filters: this launch convolves taps [in_shift, in_shift + M) 
-    int accumulate;           // ... and adds into y instead of overwriting it
 };
 
 // floor division helpers for (possibly negative) t and positive d
@@ -113,18 +109,17 @@ fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
         if constexpr (IN == 0) {
             const float2* x = reinterpret_cast<const float2*>(A.x);
             const float2* hist = reinterpret_cast<const float2*>(A.hist);
-            const long long base = b * L - Hm1 - A.in_shift;
+            const long long base = b * L - Hm1;
             if constexpr (!EDGE) {
                 const float2* xb = x + base + lane;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) v[r] = __ldcs(xb + 32 * r);
             } else {
-                const int HL = A.hist_len;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                     const long long i = base + 32 * r + lane;
                     v[r] = (i >= 0) ? (i < n ? __ldg(x + i) : make_float2(0.f, 0.f))
-                                    : ((HL + i >= 0) ? __ldg(hist + (HL + i)) : make_float2(0.f, 0.f));
+                                    : ((Hm1 + i >= 0) ? __ldg(hist + (Hm1 + i)) : make_float2(0.f, 0.f));
                 }
             }
             if constexpr (ROT) {
@@ -203,9 +198,7 @@ fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
                     const int nn = 32 * n1 + lane;
                     const long long o = obase + nn;
                     if (nn >= Hm1 && (!EDGE || o < n)) {
-                        float2 t = v[bitrev5(n1)];
-                        if (A.accumulate) t = __fadd2_rn(t, y[o]);
-                        __stcs(y + o, t);
+                        __stcs(y + o, v[bitrev5(n1)]);
                     }
                 }
             } else {
@@ -273,8 +266,7 @@ int launch_fft(const FftArgs& base_args, long long n_int, long long n_edge, cuda
         configured = true;
     }
     const long long max_ctas = (long long)ctx().sm_count * 2;
-    // edge blocks on the side stream (they only overlap the interior kernel; with `accumulate` they still touch
-    // disjoint outputs)
+    // edge blocks on the side stream (they only overlap the interior kernel and touch disjoint outputs)
     cudaStream_t side = (n_int > 0 && n_edge > 0) ? side_fork(s) : s;
     if (n_edge > 0) {
         FftArgs a = base_args;
@@ -670,20 +662,18 @@ int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long
         }
         return 1;
     }
-    for (int part = 0; part < fast->nparts; ++part) {
-        const int shift = part * Mp;
-        // interior blocks [b_lo, b_hi): b*per - (Mp-1) - shift >= 0  and  (b+1)*per <= n
-        long long b_lo = ((long long)(Mp - 1) + shift + per - 1) / per;
+    {
+        // interior blocks [b_lo, b_hi): b*per - (M-1) >= 0  and  (b+1)*per <= n
+        long long b_lo = ((long long)(Mp - 1) + per - 1) / per;
         if (b_lo < 1) b_lo = 1;
         long long b_hi = (long long)n / per;
         if (b_hi > nblocks) b_hi = nblocks;
         if (b_hi < b_lo) b_hi = b_lo;
         if (b_lo > nblocks) { b_lo = nblocks; b_hi = nblocks; }
         FftArgs a;
-        a.x = dx; a.hist = d_hist[cur]; a.y = dy; a.H = fast->d_H + (size_t)part * FF_N; a.tw = fast->d_tw; a.E = fast->d_E;
+        a.x = dx; a.hist = d_hist[cur]; a.y = dy; a.H = fast->d_H; a.tw = fast->d_tw; a.E = fast->d_E;
         a.n = (long long)n; a.b_lo = b_lo; a.b_hi = b_hi; a.nwork = 0; a.first = first;
         a.turns_fix = rot_fix; a.g0 = consumed; a.M = Mp; a.D = D;
-        a.hist_len = M - 1; a.in_shift = shift; a.accumulate = part > 0 ? 1 : 0;
         // edge work list: blocks [0, b_lo) and [b_hi, nblocks); the kernel maps e -> (e < b_lo ? e : b_hi + e - b_lo)
         const long long n_int = b_hi - b_lo, n_edge = b_lo + (nblocks - b_hi);
         const bool dec = D > 1;
