@@ -220,7 +220,7 @@ def run_b200(args):
 
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms_step, "stages_ms": dict(stage_ms)}))
+            emit(json.dumps({"profile_run": True, "ms_per_step": ms_step, "stages_ms": dict(stage_ms)}))
             bench_fir128(lib, _lib, torch, stream, args)
         return
     # ---- e2e: HOST buffers through the C ABI (pinned in, host out), H2D/D2H inside the timed call
@@ -329,7 +329,7 @@ def run_b200(args):
         result["fir128"] = bench_fir128(lib, _lib, torch, stream, args)
         result["cpu_baseline"] = cpu_baseline(lib, _lib, args)
     if rank == 0:
-        print(json.dumps(result))
+        emit(json.dumps(result))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -440,7 +440,7 @@ def run_reference(args):
         once()
     el = time.perf_counter() - t0
     v = n * steps / el / 1e6
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "WBFM-mono chain Msamples/s (input samples) @N B200; FIR-128 HBM GB/s vs roofline",
         "value": round(v, 1), "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 3)),
         "ms_per_step": round(el / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -453,7 +453,23 @@ def run_reference(args):
     }))
 
 
+_RESULT_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; see main()."""
+    out = _RESULT_OUT or sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
+    # Libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." there at init): keep a private copy of
+    # the real stdout for the result line and point fd 1 at stderr for everything else.
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
