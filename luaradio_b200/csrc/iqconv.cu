@@ -33,6 +33,20 @@ __device__ __forceinline__ float div127p5(float n) {
     return fmaf(fmaf(-q, 127.5f, n), r, q);
 }
 
+// same scheme for the 16-bit formats (n / 32767.5; all 2 x 65536 inputs checked against the double-precision result)
+__device__ __forceinline__ float div32767p5(float n) {
+    const float r = 1.0f / 32767.5f;
+    const float q = n * r;
+    return fmaf(fmaf(-q, 32767.5f, n), r, q);
+}
+
+template <int FMT, bool SWAP>
+__device__ __forceinline__ float conv16(uint32_t h) {          // h: the 16 raw bits in the low half
+    uint16_t v = (uint16_t)h;
+    if (SWAP) v = bswap16(v);
+    return FMT == F_U16 ? div32767p5((float)v - 32767.5f) : div32767p5((float)(int16_t)v);
+}
+
 template <int FMT, bool SWAP>
 __device__ __forceinline__ float conv_one(const unsigned char* p) {
     if constexpr (FMT == F_U8) return div127p5((float)p[0] - 127.5f);
@@ -40,7 +54,7 @@ __device__ __forceinline__ float conv_one(const unsigned char* p) {
     if constexpr (FMT == F_U16 || FMT == F_S16) {
         uint16_t v = *reinterpret_cast<const uint16_t*>(p);
         if (SWAP) v = bswap16(v);
-        return FMT == F_U16 ? __fdiv_rn((float)v - 32767.5f, 32767.5f) : __fdiv_rn((float)(int16_t)v, 32767.5f);
+        return FMT == F_U16 ? div32767p5((float)v - 32767.5f) : div32767p5((float)(int16_t)v);
     }
     if constexpr (FMT == F_U32 || FMT == F_S32) {
         uint32_t v = *reinterpret_cast<const uint32_t*>(p);
@@ -102,6 +116,27 @@ iqconv_u8_vec_kernel(const uint32_t* __restrict__ x, float4* __restrict__ y, lon
     }
 }
 
+// 16-bit I/Q: one 64-bit load (two samples) and one 128-bit store per thread and iteration, warp-contiguous both ways
+template <int FMT, bool SWAP>
+__global__ void __launch_bounds__(256)
+iqconv16_vec_kernel(const uint2* __restrict__ x, float4* __restrict__ y, long long n2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+        uint2 w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = __ldcs(x + i + k * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            __stcs(y + i + k * stride, make_float4(conv16<FMT, SWAP>(w[k].x), conv16<FMT, SWAP>(w[k].x >> 16),
+                                                   conv16<FMT, SWAP>(w[k].y), conv16<FMT, SWAP>(w[k].y >> 16)));
+    }
+    for (; i < n2; i += stride) {
+        const uint2 w = __ldcs(x + i);
+        __stcs(y + i, make_float4(conv16<FMT, SWAP>(w.x), conv16<FMT, SWAP>(w.x >> 16), conv16<FMT, SWAP>(w.y), conv16<FMT, SWAP>(w.y >> 16)));
+    }
+}
+
 struct FmtInfo { const char* name; int fmt; int bytes; bool big_endian; };
 const FmtInfo FORMATS[] = {
     {"u8", F_U8, 1, false}, {"s8", F_S8, 1, false},
@@ -146,8 +181,25 @@ struct IqConvBlock : Block {
                 }
                 break;
             case F_S8: iqconv_kernel<F_S8, false, 1><<<blocks, 256, 0, s>>>(x, y, nn); break;
-            case F_U16: LRB_CONV(F_U16, 2); break;
-            case F_S16: LRB_CONV(F_S16, 2); break;
+            case F_U16:
+            case F_S16:
+                if ((reinterpret_cast<uintptr_t>(x) & 7) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0 && nn >= 2) {
+                    const long long n2 = nn / 2;
+                    int vb = (int)((n2 + 255) / 256);
+                    if (vb > cap) vb = cap;
+                    const uint2* x2 = (const uint2*)x;
+                    float4* y4 = (float4*)y;
+                    if (info.fmt == F_U16) { if (sw) iqconv16_vec_kernel<F_U16, true><<<vb, 256, 0, s>>>(x2, y4, n2); else iqconv16_vec_kernel<F_U16, false><<<vb, 256, 0, s>>>(x2, y4, n2); }
+                    else { if (sw) iqconv16_vec_kernel<F_S16, true><<<vb, 256, 0, s>>>(x2, y4, n2); else iqconv16_vec_kernel<F_S16, false><<<vb, 256, 0, s>>>(x2, y4, n2); }
+                    if (nn % 2) {
+                        const unsigned char* xt = x + n2 * 8;
+                        float2* yt = y + n2 * 2;
+                        if (info.fmt == F_U16) { if (sw) iqconv_kernel<F_U16, true, 2><<<1, 32, 0, s>>>(xt, yt, 1); else iqconv_kernel<F_U16, false, 2><<<1, 32, 0, s>>>(xt, yt, 1); }
+                        else { if (sw) iqconv_kernel<F_S16, true, 2><<<1, 32, 0, s>>>(xt, yt, 1); else iqconv_kernel<F_S16, false, 2><<<1, 32, 0, s>>>(xt, yt, 1); }
+                        count_launch();
+                    }
+                } else if (info.fmt == F_U16) { LRB_CONV(F_U16, 2); } else { LRB_CONV(F_S16, 2); }
+                break;
             case F_U32: LRB_CONV(F_U32, 4); break;
             case F_S32: LRB_CONV(F_S32, 4); break;
             case F_F32: LRB_CONV(F_F32, 4); break;
