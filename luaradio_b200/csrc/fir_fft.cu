@@ -398,44 +398,44 @@ fir_fft_fdl_kernel(const __grid_constant__ FdlArgs A) {
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 128));
                 }
             }
-            const int s0 = (g - (FD_MAXPC - 1) + R * 4) % R;   // slot of block g - 3 (blocks before g - (PC-1) are never read)
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int row = (2 * warp + half) * 32 + lane;
-                const float4* ring4 = reinterpret_cast<const float4*>(ring);
-                float4 Hr[FD_MAXPC];
+            // slot offsets (float4 units) of blocks g-3 .. g+7 and of the FD_W output slots, shared by both row halves.
+            // Blocks of this group beyond the end of the run hold stale spectra; their Y lands in slots nobody reads.
+            int xoff[FD_W + FD_MAXPC - 1], yoff[FD_W];
+            {
+                int sl = (g - (FD_MAXPC - 1) + R * 4) % R;
 #pragma unroll
-                for (int pp = 0; pp < FD_MAXPC; ++pp)
-                    if (pp < PC) Hr[pp] = __ldg(reinterpret_cast<const float4*>(A.H) + pp * (FF_N / 2) + row);
-                float4 Xr[FD_W + FD_MAXPC - 1];
-                int sl = s0;
-#pragma unroll
-                for (int i = 0; i < FD_W + FD_MAXPC - 1; ++i) {
-                    if (i >= FD_MAXPC - PC) Xr[i] = ring4[sl * (FF_XCH / 2) + row];
-                    sl = sl + 1 == R ? 0 : sl + 1;
-                }
+                for (int i = 0; i < FD_W + FD_MAXPC - 1; ++i) { xoff[i] = sl * (FF_XCH / 2); sl = sl + 1 == R ? 0 : sl + 1; }
                 int so = (g + FD_W) % R;
 #pragma unroll
-                for (int j = 0; j < FD_W; ++j) {
-                    if (g + j < nrel) {
-                        float4 a = Xr[j + FD_MAXPC - 1];
-                        float2 t0 = __fmul2_rn(make_float2(-a.y, a.x), make_float2(Hr[0].y, Hr[0].y));
-                        float2 ye = __ffma2_rn(make_float2(a.x, a.y), make_float2(Hr[0].x, Hr[0].x), t0);
-                        float2 t1 = __fmul2_rn(make_float2(-a.w, a.z), make_float2(Hr[0].w, Hr[0].w));
-                        float2 yo = __ffma2_rn(make_float2(a.z, a.w), make_float2(Hr[0].z, Hr[0].z), t1);
+                for (int j = 0; j < FD_W; ++j) { yoff[j] = so * (FF_XCH / 2); so = so + 1 == R ? 0 : so + 1; }
+            }
+            const float4* ring4 = reinterpret_cast<const float4*>(ring);
+            float4* ring4w = reinterpret_cast<float4*>(ring);
 #pragma unroll
-                        for (int pp = 1; pp < FD_MAXPC; ++pp) {
-                            if (pp < PC) {
-                                a = Xr[j + FD_MAXPC - 1 - pp];
-                                ye = __ffma2_rn(make_float2(a.x, a.y), make_float2(Hr[pp].x, Hr[pp].x), ye);
-                                ye = __ffma2_rn(make_float2(-a.y, a.x), make_float2(Hr[pp].y, Hr[pp].y), ye);
-                                yo = __ffma2_rn(make_float2(a.z, a.w), make_float2(Hr[pp].z, Hr[pp].z), yo);
-                                yo = __ffma2_rn(make_float2(-a.w, a.z), make_float2(Hr[pp].w, Hr[pp].w), yo);
-                            }
-                        }
-                        reinterpret_cast<float4*>(ring)[so * (FF_XCH / 2) + row] = make_float4(ye.x, ye.y, yo.x, yo.y);
+            for (int half = 0; half < 2; ++half) {
+                const int row = (2 * warp + half) * 32 + lane;
+                float4 Hr[PC];
+#pragma unroll
+                for (int pp = 0; pp < PC; ++pp) Hr[pp] = __ldg(reinterpret_cast<const float4*>(A.H) + pp * (FF_N / 2) + row);
+                float4 Xr[FD_W + FD_MAXPC - 1];
+#pragma unroll
+                for (int i = FD_MAXPC - PC; i < FD_W + FD_MAXPC - 1; ++i) Xr[i] = ring4[xoff[i] + row];
+#pragma unroll
+                for (int j = 0; j < FD_W; ++j) {
+                    float4 a = Xr[j + FD_MAXPC - 1];
+                    float2 t0 = __fmul2_rn(make_float2(-a.y, a.x), make_float2(Hr[0].y, Hr[0].y));
+                    float2 ye = __ffma2_rn(make_float2(a.x, a.y), make_float2(Hr[0].x, Hr[0].x), t0);
+                    float2 t1 = __fmul2_rn(make_float2(-a.w, a.z), make_float2(Hr[0].w, Hr[0].w));
+                    float2 yo = __ffma2_rn(make_float2(a.z, a.w), make_float2(Hr[0].z, Hr[0].z), t1);
+#pragma unroll
+                    for (int pp = 1; pp < PC; ++pp) {
+                        a = Xr[j + FD_MAXPC - 1 - pp];
+                        ye = __ffma2_rn(make_float2(a.x, a.y), make_float2(Hr[pp].x, Hr[pp].x), ye);
+                        ye = __ffma2_rn(make_float2(-a.y, a.x), make_float2(Hr[pp].y, Hr[pp].y), ye);
+                        yo = __ffma2_rn(make_float2(a.z, a.w), make_float2(Hr[pp].z, Hr[pp].z), yo);
+                        yo = __ffma2_rn(make_float2(-a.w, a.z), make_float2(Hr[pp].w, Hr[pp].w), yo);
                     }
-                    so = so + 1 == R ? 0 : so + 1;
+                    ring4w[yoff[j] + row] = make_float4(ye.x, ye.y, yo.x, yo.y);
                 }
             }
         }
