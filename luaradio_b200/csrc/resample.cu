@@ -81,7 +81,8 @@ interp_fir_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __rest
     }
 }
 
-// ---- Interpolator (D == 1, 2 <= L <= 8): register-tiled polyphase kernel.  A thread owns IT_R consecutive inputs and
+// ---- Interpolator (D == 1) and small-D rational resampler (D <= 4), 2 <= L <= 8: register-tiled polyphase kernel
+// (for D > 1 all phases are computed and D-1 of D dropped at the store: still ~3x faster than one thread per kept output).  A thread owns IT_R consecutive inputs and
 // all L phases (IT_R * L accumulators); per tap row t it needs x[i - t] for its IT_R inputs, a window that slides by one
 // sample per row, so one new shared-memory value per row feeds IT_R * L multiply-adds.  The window is held as two aligned
 // register chunks A = x[s0 - tb*R .. +R) and B = x[s0 - (tb+1)*R .. +R): every index below is a compile-time constant and
@@ -103,7 +104,7 @@ constexpr int IT_TILE = IT_R * IT_THREADS;        // inputs per CTA tile
 template <typename T, int L, bool SCALE>
 __global__ void __launch_bounds__(IT_THREADS)
 interp_tiled_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __restrict__ y, const float* __restrict__ taps_tp,
-                    long long n, int Hn, int Tt, float c) {
+                    long long n, int Hn, int Tt, float c, int D, long long J0, long long m_lo) {
     extern __shared__ __align__(16) unsigned char it_smem[];
     float* hs = reinterpret_cast<float*>(it_smem);                       // [Tt][L]
     T* xs = reinterpret_cast<T*>(it_smem + (((size_t)Tt * L * sizeof(float) + 15) & ~(size_t)15));   // [Tt + IT_TILE], xs[Tt + j] = x[tile0 + j]
@@ -149,12 +150,32 @@ interp_tiled_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __re
             for (int r = 0; r < IT_R; ++r) A[r] = B[r];
         }
         const long long i0 = tile0 + (long long)tid * IT_R;
+        if (D == 1) {
 #pragma unroll
-        for (int r = 0; r < IT_R; ++r) {
-            if (i0 + r < n) {
-                T* yo = y + (i0 + r) * L;
+            for (int r = 0; r < IT_R; ++r) {
+                if (i0 + r < n) {
+                    T* yo = y + (i0 + r) * L;
 #pragma unroll
-                for (int p = 0; p < L; ++p) yo[p] = acc[r][p];
+                    for (int p = 0; p < L; ++p) yo[p] = acc[r][p];
+                }
+            }
+        } else {
+            // rational resampling with a small D: every phase was computed, keep the upsampled indices J = 0 (mod D).
+            // J0 = global upsampled index of this call's first input, m_lo = global index of this call's first output.
+            long long J = J0 + i0 * L;
+            long long m = (J + D - 1) / D;                         // first kept output at or after J
+            int gap = (int)(m * D - J);                            // its distance in upsampled samples
+#pragma unroll
+            for (int r = 0; r < IT_R; ++r) {
+#pragma unroll
+                for (int p = 0; p < L; ++p) {
+                    if (gap == 0) {
+                        if (i0 + r < n) y[m - m_lo] = acc[r][p];
+                        ++m;
+                        gap = D;
+                    }
+                    --gap;
+                }
             }
         }
     }
@@ -226,7 +247,7 @@ int InterpFirBlock::init() {
     LRB_CHECK(cudaMalloc(&d_taps, sizeof(float) * (size_t)M));
     LRB_CHECK(cudaMemcpy(d_taps, h_taps.data(), sizeof(float) * (size_t)M, cudaMemcpyHostToDevice));
     Tt = ((M + L - 1) / L + IT_R - 1) / IT_R * IT_R;
-    if (D == 1 && L >= 2 && L <= 8 && (size_t)Tt * L * sizeof(float) + (size_t)(Tt + IT_TILE) * in_size + 16 <= 48 * 1024) {
+    if (D <= 4 && L >= 2 && L <= 8 && (size_t)Tt * L * sizeof(float) + (size_t)(Tt + IT_TILE) * in_size + 16 <= 48 * 1024) {
         std::vector<float> tp((size_t)Tt * L, 0.0f);
         for (int k = 0; k < M; ++k) tp[(size_t)(k / L) * L + (k % L)] = h_taps[k];
         LRB_CHECK(cudaMalloc(&d_taps_tp, sizeof(float) * tp.size()));
@@ -250,11 +271,11 @@ int InterpFirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaS
     const long long no = m_hi - m_lo;
     *n_out = (size_t)no;
     if (n == 0) return 0;
-    if (no > 0 && D == 1 && L >= 2 && L <= 8 && d_taps_tp) {
+    if (no > 0 && d_taps_tp) {
         const long long ntiles = ((long long)n + IT_TILE - 1) / IT_TILE;
         const int g = (int)std::min<long long>(ntiles, (long long)ctx().sm_count * 8);
         const size_t smem = (((size_t)Tt * L * sizeof(float) + 15) & ~(size_t)15) + (size_t)(Tt + IT_TILE) * in_size;
-#define LRB_IT2(T, LL, S) interp_tiled_kernel<T, LL, S><<<g, IT_THREADS, smem, s>>>((const T*)dx, (const T*)d_hist[cur], (T*)dy, d_taps_tp, (long long)n, Hn, Tt, scale)
+#define LRB_IT2(T, LL, S) interp_tiled_kernel<T, LL, S><<<g, IT_THREADS, smem, s>>>((const T*)dx, (const T*)d_hist[cur], (T*)dy, d_taps_tp, (long long)n, Hn, Tt, scale, D, (long long)consumed * L, m_lo)
 #define LRB_IT(LL) \
         if (complex_data) { if (has_scale) LRB_IT2(float2, LL, true); else LRB_IT2(float2, LL, false); } \
         else { if (has_scale) LRB_IT2(float, LL, true); else LRB_IT2(float, LL, false); }

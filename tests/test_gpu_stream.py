@@ -409,7 +409,8 @@ def test_nbfm_am_ssb_demodulators(chunk):
         radio.SSBDemodulator("dsb")
 
 
-@pytest.mark.parametrize("L,D,M", [(2, 1, 128), (3, 1, 128), (7, 5, 128), (2, 3, 128), (4, 25, 200), (160, 147, 1024), (5, 1, 33)])
+@pytest.mark.parametrize("L,D,M", [(2, 1, 128), (3, 1, 128), (7, 5, 128), (2, 3, 128), (3, 2, 128), (8, 4, 100), (5, 4, 64), (4, 25, 200),
+                                   (160, 147, 1024), (5, 1, 33)])
 @pytest.mark.parametrize("cplx", [True, False])
 def test_interpolator_and_rational_resampler_stream(L, D, M, cplx):
     """InterpolatorBlock / RationalResamplerBlock as one polyphase kernel (fused) and as four separate kernels (unfused)
