@@ -3,6 +3,7 @@
 -- the file named in its comment.  Apply with  require('radio_b200.blocks_patch')(require('radio')).
 
 local math = require('math')
+local ffi = require('ffi')
 local platform = require('radio.core.platform')
 local types = require('radio.types')
 local b200 = require('radio_b200.platform')
@@ -63,4 +64,61 @@ return function (radio)
         self.out = types.Float32.vector()
     end
     radio.ComplexToRealBlock.process = b200.process
+
+    -- radio/blocks/signal/upsampler.lua:36-52 and multiplyconstant.lua:44-70 (resampling family, SURVEY 8f row 4).
+    -- InterpolatorBlock / RationalResamplerBlock stay the composites they are; in a GPU sub-graph the three or four
+    -- handles are committed to one polyphase kernel (composite_patch.lua -> lrb200_graph_commit).
+    function radio.UpsamplerBlock:initialize()
+        local data_type = self:get_input_type()
+        self.handle = b200.own(lib.lrb200_upsample_create(self.factor, data_type == types.ComplexFloat32 and 8 or 4, b200.HOST), "upsampler")
+        self.out = data_type.vector()
+    end
+    radio.UpsamplerBlock.process = b200.process
+    function radio.MultiplyConstantBlock:initialize()
+        local cplx_data = self:get_input_type() == types.ComplexFloat32
+        local c = self.constant
+        local cplx_const = ffi.istype(types.ComplexFloat32, c)
+        self.handle = b200.own(lib.lrb200_mulconst_create(cplx_const and c.real or c.value, cplx_const and c.imag or 0,
+                                                          cplx_data and 1 or 0, cplx_const and 1 or 0, b200.HOST), "mulconst")
+        self.out = self:get_output_type().vector()
+    end
+    radio.MultiplyConstantBlock.process = b200.process
+    radio.MultiplyConstantBlock.process_complex_by_real = b200.process
+
+    -- File sample formats (SURVEY 8f row 1).  Sources keep their fread(); the swap + (value - offset)/scale loop of
+    -- radio/blocks/sources/iqfile.lua:96-108 / realfile.lua:86-104 becomes one call on the raw chunk.
+    local function source_process(create, what)
+        return function (self)
+            local n = tonumber(ffi.C.fread(self.raw_samples.data, ffi.sizeof(self.raw_samples.data_type), self.raw_samples.length, self.file))
+            if n == 0 then
+                if ffi.C.feof(self.file) ~= 0 and self.repeat_on_eof then ffi.C.rewind(self.file) else return nil end
+            end
+            self.handle = self.handle or b200.own(create(self.format_name, b200.HOST), what)
+            local out, n_out = self.out:resize(n), ffi.new("size_t[1]")
+            if lib.lrb200_block_execute(self.handle, self.raw_samples.data, n, out.data, n_out) ~= 0 then
+                error(what .. ": " .. ffi.string(lib.lrb200_last_error()))
+            end
+            return out
+        end
+    end
+    radio.IQFileSource.process = source_process(lib.lrb200_iqconv_create, "iqconv")
+    radio.RealFileSource.process = source_process(lib.lrb200_realconv_create, "realconv")
+    -- Sinks (radio/blocks/sinks/iqfile.lua:66-88, realfile.lua, wavfile.lua:170-194 for one channel): convert, then fwrite.
+    local function sink_process(create, what)
+        return function (self, x)
+            self.handle = self.handle or b200.own(create(self.format_name, b200.HOST), what)
+            self.raw_samples:resize(x.length)
+            local n_out = ffi.new("size_t[1]")
+            if lib.lrb200_block_execute(self.handle, x.data, x.length, self.raw_samples.data, n_out) ~= 0 then
+                error(what .. ": " .. ffi.string(lib.lrb200_last_error()))
+            end
+            if ffi.C.fwrite(self.raw_samples.data, ffi.sizeof(self.raw_samples.data_type), x.length, self.file) ~= x.length then
+                error("fwrite(): " .. ffi.string(ffi.C.strerror(ffi.errno())))
+            end
+            self.count = (self.count or 0) + x.length           -- WAVFileSink:cleanup() fills the header sizes from it
+        end
+    end
+    radio.IQFileSink.process = sink_process(lib.lrb200_iqsink_create, "iqsink")
+    radio.RealFileSink.process = sink_process(lib.lrb200_realsink_create, "realsink")
+    -- format_name: the constructor keeps the format string next to self.format (one added line in each instantiate()).
 end
