@@ -49,6 +49,7 @@ struct FirBlock : Block {
     uint64_t rot_fix = 0;
     FirFast* fast = nullptr;
     PolyTaps* poly = nullptr;
+    std::string label;                // owns `name` when a graph rewrite renames the block
 
     FirBlock(FirKind k, const void* taps_host, unsigned ntaps, unsigned decim, bool dev);
     void set_rotation(double turns_per_sample) { rotate = true; rot_turns = turns_per_sample; rot_fix = turns_to_fix(turns_per_sample); }
@@ -181,11 +182,15 @@ struct lrb200_block_s { lrb::Block* impl; };
 namespace lrb {
 // tuner.cu: register-tiled polyphase decimating FIR (complex in, real taps), optional fused rotator.
 // Returns 1 if the (M, D) shape is supported and the launch was enqueued, 0 if unsupported, <0 on error.
-PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table = false);
+PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table = false,
+                            bool real_data = false);
 void polyphase_release(PolyTaps* p);
 int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist, long long n, float2* y,
                           long long first, long long n_out, bool rotate, uint64_t turns_fix, uint64_t g0,
                           cudaStream_t s);
+// real input, real taps, decimating (x / hist / y are float32)
+int launch_polyphase_rrrf(const PolyTaps* p, const float* x, const float* hist, long long n, float* y,
+                          long long first, long long n_out, cudaStream_t s);
 // tuner.cu: fused FrequencyTranslator -> FIR(crcf) -> Downsampler; returns nullptr (with the error set) on failure
 // iqconv.cu: IQFileSource sample format -> ComplexFloat32 (nullptr + error for an unknown format)
 Block* make_iqconv(const char* format, bool dev);

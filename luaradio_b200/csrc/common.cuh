@@ -9,6 +9,8 @@
 
 namespace lrb {
 
+#define LRB_MAX_DEVICES 16        // per-device "function attributes set" flags (power of two)
+
 struct Ctx {
     int device = -1;
     int sm_count = 148;

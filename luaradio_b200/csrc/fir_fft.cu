@@ -256,7 +256,8 @@ fir_fft1024_kernel(const __grid_constant__ FftArgs A) {
 
 template <int IN, bool ROT, bool DEC>
 int launch_fft(const FftArgs& base_args, long long n_int, long long n_edge, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_dev[LRB_MAX_DEVICES] = {false};     // function attributes are per device
+    bool& configured = configured_dev[ctx().device & (LRB_MAX_DEVICES - 1)];
     constexpr size_t smem = (size_t)((ROT ? 3 : 2) * FF_N + FF_WARPS * FF_XCH) * sizeof(float2);
     auto ki = fir_fft1024_kernel<IN, false, ROT, DEC>;
     auto ke = fir_fft1024_kernel<IN, true, ROT, DEC>;
@@ -480,7 +481,8 @@ fir_fft_fdl_kernel(const __grid_constant__ FdlArgs A) {
 
 template <int PC>
 int launch_fdl_pc(FdlArgs a, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_dev[LRB_MAX_DEVICES] = {false};     // function attributes are per device
+    bool& configured = configured_dev[ctx().device & (LRB_MAX_DEVICES - 1)];
     constexpr size_t smem = (size_t)(FF_N + (FD_W + PC - 1) * FF_XCH) * sizeof(float2);
     auto ki = fir_fft_fdl_kernel<false, PC>;
     auto ke = fir_fft_fdl_kernel<true, PC>;
@@ -540,6 +542,7 @@ static constexpr int FFT_MAX_TAPS = 513;       // L >= 512: at most half of ever
 int FirBlock::fast_init() {
     // register-tiled direct kernel: decimators with <= 128 taps and plain FIRs with <= 32 taps (complex in, real taps)
     if (kind == FIR_CRCF && !rotate) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
+    if (kind == FIR_RRRF && D > 1) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0, false, true);
     if (kind == FIR_HILBERT && D != 1) return 0;
     const bool long_filter = M > FFT_MAX_TAPS;
     // long filters: complex-input, no fused decimation/translator -> P partitions of 512 taps, P passes over x
@@ -631,6 +634,8 @@ int FirBlock::set_algorithm(int a) {
 }
 
 int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long long n_out, cudaStream_t s) {
+    if (poly && algo != LRB200_FIR_FFT && kind == FIR_RRRF)
+        return launch_polyphase_rrrf(poly, (const float*)dx, (const float*)d_hist[cur], (long long)n, (float*)dy, first, n_out, s);
     if (poly && algo != LRB200_FIR_FFT)
         return launch_polyphase_crcf(poly, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, (float2*)dy,
                                      first, n_out, false, 0, consumed, s);

@@ -73,6 +73,7 @@ struct Graph {
         while (i < blocks.size()) {
             Block* b = blocks[i];
             Block* st = b;
+            Block* st2 = nullptr;        // a rewrite may turn a run of blocks into two stages
             size_t used = 1;
             if (fuse) {
                 RotatorBlock* rot = dynamic_cast<RotatorBlock*>(b);
@@ -92,7 +93,7 @@ struct Graph {
                         // translator folded into the overlap-save kernel (any taps, complex taps included)
                         FirBlock* nf = new (std::nothrow) FirBlock(f2->kind, f2->h_taps.data(), (unsigned)f2->M, (unsigned)(d3 ? d3->D : 1), true);
                         if (!nf) { set_error("out of memory"); return -1; }
-                        nf->set_rotation(rot->turns);
+                        nf->set_rotation(rot->turns);      // (the fused translator forces the overlap-save path: algo is moot)
                         nf->name = f2->kind == FIR_CCCF ? "rot+fir_cccf" : "rot+fir_crcf";
                         if (nf->init() != 0) { delete nf; return -1; }
                         fused.push_back(nf); st = nf; used = d3 ? 3 : 2;
@@ -111,15 +112,66 @@ struct Graph {
                         if (d3 && d3->in_size != f2->out_size) d3 = nullptr;
                         InterpFirBlock* nb = new (std::nothrow) InterpFirBlock(f2->kind == FIR_CRCF, (const float*)f2->h_taps.data(), f2->M,
                                                                                up->L, d3 ? d3->D : 1, sc != nullptr, sc ? sc->cre : 1.0f, true);
-                        if (!nb || nb->init() != 0) { delete nb; return -1; }
+                        if (!nb) { set_error("out of memory"); return -1; }
+                        if (nb->init() != 0) { delete nb; return -1; }
                         fused.push_back(nb); st = nb; used = (j - i) + 2 + (d3 ? 1 : 0);
+                    }
+                }
+                if (used == 1 && fir && fir->D == 1 && fir->kind == FIR_RRRF && i + 2 < blocks.size()) {
+                    // FIR(h) -> single-pole IIR (b, c) -> Downsampler(D), all real (the chain's audio tail,
+                    // examples/rtlsdr_wbfm_mono.lua:15-18; iirfilter.lua:147-179; downsampler.lua:45-53).
+                    // y[n] = c y[n-1] + v[n], v = b * u, u = h * x.  Unrolling the recurrence D times:
+                    //     y[n] = c^D y[n-D] + sum_{i<D} c^i v[n-i]
+                    // so the kept samples z[m] = y[mD] obey  z[m] = c^D z[m-1] + w[mD]  with  w = (h * b * [1, c, .., c^(D-1)]) * x:
+                    // ONE decimating FIR with M + nb + D - 2 taps (only kept outputs computed) and a pole c^D at the
+                    // output rate, instead of a full-rate FIR and a full-rate recurrence that both compute D times more
+                    // samples than the Downsampler keeps.  Zero initial state on both sides, so the streams are equal
+                    // from the first sample; the taps are designed in float64 from the float32 coefficients.
+                    IirBlock* i2 = dynamic_cast<IirBlock*>(blocks[i + 1]);
+                    DownsampleBlock* d3 = dynamic_cast<DownsampleBlock*>(blocks[i + 2]);
+                    if (i2 && !i2->complex_data && i2->D == 1 && d3 && d3->in_size == 4 && d3->D > 1) {
+                        const int Dd = d3->D, nbb = i2->nb;
+                        std::vector<double> g((size_t)(nbb + Dd - 1), 0.0);
+                        double cp = 1.0;
+                        for (int k = 0; k < Dd; ++k) {
+                            for (int j = 0; j < nbb; ++j) g[(size_t)(k + j)] += cp * (double)i2->b[j];
+                            cp *= (double)i2->c;
+                        }
+                        const float* h = (const float*)fir->h_taps.data();
+                        const int Mc = fir->M + (int)g.size() - 1;
+                        std::vector<float> hc((size_t)Mc);
+                        for (int t = 0; t < Mc; ++t) {
+                            double acc = 0.0;
+                            for (int k = 0; k < (int)g.size(); ++k)
+                                if (t - k >= 0 && t - k < fir->M) acc += g[(size_t)k] * (double)h[t - k];
+                            hc[(size_t)t] = (float)acc;
+                        }
+                        FirBlock* nf = new (std::nothrow) FirBlock(FIR_RRRF, hc.data(), (unsigned)Mc, (unsigned)Dd, true);
+                        if (!nf) { set_error("out of memory"); return -1; }
+                        nf->set_algorithm(fir->algo);
+                        if (nf->init() != 0) { delete nf; return -1; }
+                        if (nf->poly) {      // only worth it when the polyphase kernel has this shape
+                            const float one = 1.0f, a2[2] = {1.0f, (float)(-cp)};     // cp == c^D
+                            IirBlock* ni = new (std::nothrow) IirBlock(false, &one, 1, a2, 2, true);
+                            if (!ni) { delete nf; set_error("out of memory"); return -1; }
+                            if (ni->init() != 0) { delete nf; delete ni; return -1; }
+                            nf->label = "fir*iir1_rrrf(" + std::to_string(Mc) + ",/" + std::to_string(Dd) + ")";
+                            nf->name = nf->label.c_str();
+                            ni->name = "pole_rrrf";
+                            fused.push_back(nf); fused.push_back(ni);
+                            st = nf; st2 = ni; used = 3;
+                        } else {
+                            delete nf;
+                        }
                     }
                 }
                 if (used == 1 && fir && fir->D == 1 && fir->kind != FIR_HILBERT && i + 1 < blocks.size()) {
                     DownsampleBlock* d2 = dynamic_cast<DownsampleBlock*>(blocks[i + 1]);
                     if (d2 && d2->in_size == fir->out_size) {
                         FirBlock* nf = new (std::nothrow) FirBlock(fir->kind, fir->h_taps.data(), (unsigned)fir->M, (unsigned)d2->D, true);
-                        if (!nf || nf->init() != 0) { delete nf; return -1; }
+                        if (!nf) { set_error("out of memory"); return -1; }
+                        nf->set_algorithm(fir->algo);      // FIRFilterBlock(taps, use_fft) survives the fusion
+                        if (nf->init() != 0) { delete nf; return -1; }
                         fused.push_back(nf); st = nf; used = 2;
                     }
                 }
@@ -139,6 +191,7 @@ struct Graph {
             if (!desc.empty()) desc += " | ";
             desc += st->name;
             if (used > 1) { desc += "[fused x"; desc += std::to_string(used); desc += "]"; }
+            if (st2) { stages.push_back(st2); desc += " | "; desc += st2->name; }
             i += used;
         }
         for (size_t k = 0; k + 1 < stages.size(); ++k) {

@@ -68,6 +68,18 @@ __device__ __forceinline__ void load9(const float2* __restrict__ xb, float2 (&xv
     for (int i = 0; i < 9; ++i) xv[i] = __ldg(xb + i);
 }
 
+// x[b .. b+8) for a pure pole (NBT = 1): two 128-bit loads
+__device__ __forceinline__ void load8(const float* __restrict__ xb, float (&xv)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(xb));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(xb + 4));
+    xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w;
+    xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+}
+__device__ __forceinline__ void load8(const float2* __restrict__ xb, float2 (&xv)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xv[i] = __ldg(xb + i);
+}
+
 // NBT: compile-time number of feed-forward taps (2 for every single-pole design of the reference; IIR_MAX_NB = generic).
 // With the generic 9-slot loops the kernel was instruction-bound (ncu: 74 % issue-active, ~70 instr per sample).
 template <typename T, bool LOCAL, int NBT>
@@ -126,6 +138,12 @@ next_tile:
 #pragma unroll
                 for (int i = 0; i < 9; ++i) xv[i] = __ldg(xb + i);
             }
+        } else if constexpr (NBT == 1 && IIR_V == 8) {
+            if (vec_ok) load8(xb, xv);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xv[i] = __ldg(xb + i);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < IIR_V + NBT - 1; ++i) xv[i] = __ldg(xb + i);
@@ -165,6 +183,12 @@ next_tile:
                     else {
 #pragma unroll
                         for (int i = 0; i < 9; ++i) xnext[i] = __ldg(xb + i);
+                    }
+                } else if constexpr (NBT == 1 && IIR_V == 8) {
+                    if (vec_ok) load8(xb, xnext);
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xnext[i] = __ldg(xb + i);
                     }
                 } else {
 #pragma unroll
@@ -353,8 +377,8 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
 #define LRB_IIR_LOCAL(TT, NN)                                                                                   \
         iir1_scan_kernel<TT, true, NN><<<grid, IIR_THREADS, 0, s>>>((const TT*)x, n, (TT*)y, P, (const TT*)xhist_in, \
             (TT*)xhist_out, (const TT*)ystate_in, (TT*)ystate_out, first, D, nullptr, nullptr, nullptr, nullptr, (unsigned)tiles)
-        if (complex_data) { if (nb == 2) LRB_IIR_LOCAL(float2, 2); else LRB_IIR_LOCAL(float2, IIR_MAX_NB); }
-        else { if (nb == 2) LRB_IIR_LOCAL(float, 2); else LRB_IIR_LOCAL(float, IIR_MAX_NB); }
+        if (complex_data) { if (nb == 2) LRB_IIR_LOCAL(float2, 2); else if (nb == 1) LRB_IIR_LOCAL(float2, 1); else LRB_IIR_LOCAL(float2, IIR_MAX_NB); }
+        else { if (nb == 2) LRB_IIR_LOCAL(float, 2); else if (nb == 1) LRB_IIR_LOCAL(float, 1); else LRB_IIR_LOCAL(float, IIR_MAX_NB); }
 #undef LRB_IIR_LOCAL
         count_launch();
         LRB_CHECK(cudaGetLastError());
@@ -370,8 +394,8 @@ int launch_iir1(bool complex_data, const void* x, long long n, void* y, const fl
 #define LRB_IIR_SCAN(TT, NN)                                                                                    \
     iir1_scan_kernel<TT, false, NN><<<tiles, IIR_THREADS, 0, s>>>((const TT*)x, n, (TT*)y, P, (const TT*)xhist_in,  \
         (TT*)xhist_out, (const TT*)ystate_in, (TT*)ystate_out, first, D, w->ticket, w->flags, (TT*)w->agg, (TT*)w->pfx, w->epoch)
-    if (complex_data) { if (nb == 2) LRB_IIR_SCAN(float2, 2); else LRB_IIR_SCAN(float2, IIR_MAX_NB); }
-    else { if (nb == 2) LRB_IIR_SCAN(float, 2); else LRB_IIR_SCAN(float, IIR_MAX_NB); }
+    if (complex_data) { if (nb == 2) LRB_IIR_SCAN(float2, 2); else if (nb == 1) LRB_IIR_SCAN(float2, 1); else LRB_IIR_SCAN(float2, IIR_MAX_NB); }
+    else { if (nb == 2) LRB_IIR_SCAN(float, 2); else if (nb == 1) LRB_IIR_SCAN(float, 1); else LRB_IIR_SCAN(float, IIR_MAX_NB); }
 #undef LRB_IIR_SCAN
     count_launch();
     LRB_CHECK(cudaGetLastError());

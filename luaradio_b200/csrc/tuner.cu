@@ -100,15 +100,24 @@ __device__ __forceinline__ void static_for(F&& f) {
 template <bool DISC>
 struct TileStride { static constexpr int TS = DISC ? PT_TO - 2 : PT_TO; };
 
-template <int D, int Q, bool ROT, bool DISC, bool EDGE>
+// REAL: real input, real taps, real output (the audio low-pass + de-emphasis + Downsampler(5) stage of the chain,
+// firfilter.lua:147-163 behind the noble identity, see graph.cu).  The two lanes of every packed register are two
+// INDEPENDENT real streams: element e of the staged tile is (xr[B + e], xr[B + PT_TO*D + e]), so lane 0 computes the
+// tile's first PT_TO outputs and lane 1 the next PT_TO, and every FFMA2 of the unchanged compute phase is two useful
+// real MACs.  x / hist then point to float32 data.
+template <int D, int Q, bool ROT, bool DISC, bool EDGE, bool REAL = false>
 __global__ void __launch_bounds__(PT_THREADS, LRB_PT_CTAS)
 polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, long long n,
                       void* __restrict__ yv, long long n_out, const __grid_constant__ PolyParams P,
                       long long t_lo, long long t_hi,
                       const float2* __restrict__ prev_in, float2* __restrict__ prev_out, float inv_gain) {
     using S = PolyShape<D, Q>;
-    constexpr int TS = TileStride<DISC>::TS;
+    static_assert(!(REAL && (ROT || DISC)), "the real-stream variant has no translator / discriminator");
+    constexpr int TS = REAL ? 2 * PT_TO : TileStride<DISC>::TS;    // outputs per tile
     constexpr int NPRE = S::ITERS < LRB_PT_PREFETCH ? S::ITERS : LRB_PT_PREFETCH;   // pairs prefetched across the compute phase
+    constexpr int LANE1 = PT_TO * D;                               // REAL: input distance between the two lanes' streams
+    const float* __restrict__ xr = reinterpret_cast<const float*>(x);
+    const float* __restrict__ histr = reinterpret_cast<const float*>(hist);
     extern __shared__ __align__(16) float2 smem[];
     __shared__ float2 s_edge[PT_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -128,12 +137,22 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
 
     // staging addresses: pair u = tid + 128*it holds samples e = 2u, 2u+1 -> padded element 2u + 2*floor(2u / RD)
     // (RD is even, so a pair never straddles a padding gap and stays 16-byte aligned)
+    // pair u = tid + k*PT_THREADS of the tile whose first input index is Bt, as (elem 2u, elem 2u+1)
+    auto ld_pair = [&](long long Bt, int k) -> float4 {
+        if constexpr (REAL) {
+            const float2* pa = reinterpret_cast<const float2*>(xr + Bt) + (tid + k * PT_THREADS);
+            const float2 a = __ldcs(pa), b = __ldcs(pa + LANE1 / 2);
+            return make_float4(a.x, b.x, a.y, b.y);
+        } else {
+            return __ldcs(reinterpret_cast<const float4*>(x + Bt) + (tid + k * PT_THREADS));
+        }
+    };
     float4 pre[NPRE];
     if constexpr (!EDGE) {
         if (widx < n_work) {
-            const float4* x4 = reinterpret_cast<const float4*>(x + (P.off + tile_of(widx) * (long long)(TS * D))) + tid;
+            const long long Bt = P.off + tile_of(widx) * (long long)(TS * D);
 #pragma unroll
-            for (int k = 0; k < NPRE; ++k) pre[k] = __ldcs(x4 + k * PT_THREADS);
+            for (int k = 0; k < NPRE; ++k) pre[k] = ld_pair(Bt, k);
         }
     }
 
@@ -157,11 +176,10 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         if constexpr (!EDGE) {
             // the first NPRE pairs were prefetched during the previous tile's compute phase; the rest of the tile
             // is requested now and lands while those are rotated and stored
-            const float4* x4 = reinterpret_cast<const float4*>(x + B) + tid;
             constexpr int REST = (S::ITERS - NPRE) < PT_BATCH ? (S::ITERS - NPRE) : PT_BATCH;
             float4 rest[REST > 0 ? REST : 1];
 #pragma unroll
-            for (int k = 0; k < REST; ++k) rest[k] = __ldcs(x4 + (NPRE + k) * PT_THREADS);
+            for (int k = 0; k < REST; ++k) rest[k] = ld_pair(B, NPRE + k);
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], k);
 #pragma unroll
@@ -171,7 +189,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 float4 buf[PT_BATCH];
 #pragma unroll
                 for (int k = 0; k < PT_BATCH; ++k)
-                    if (it0 + k < S::ITERS) buf[k] = __ldcs(x4 + (it0 + k) * PT_THREADS);
+                    if (it0 + k < S::ITERS) buf[k] = ld_pair(B, it0 + k);
 #pragma unroll
                 for (int k = 0; k < PT_BATCH; ++k)
                     if (it0 + k < S::ITERS) stage_pair(buf[k], it0 + k);
@@ -180,6 +198,13 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
 #pragma unroll 2
             for (int it = 0; it < S::ITERS; ++it) {
                 const long long i0 = B + 2LL * (tid + it * PT_THREADS);
+                if constexpr (REAL) {
+                    auto g = [&](long long i) -> float {
+                        return (i >= 0) ? (i < n ? __ldg(xr + i) : 0.f) : ((Hm1 + i >= 0) ? __ldg(histr + (Hm1 + i)) : 0.f);
+                    };
+                    stage_pair(make_float4(g(i0), g(i0 + LANE1), g(i0 + 1), g(i0 + 1 + LANE1)), it);
+                    continue;
+                }
                 const float2 a = (i0 >= 0) ? (i0 < n ? __ldg(x + i0) : make_float2(0.f, 0.f))
                                            : ((Hm1 + i0 >= 0) ? __ldg(hist + (Hm1 + i0)) : make_float2(0.f, 0.f));
                 const long long i1 = i0 + 1;
@@ -194,9 +219,9 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         if constexpr (!EDGE) {
             const long long nidx = widx + gridDim.x;
             if (nidx < n_work) {
-                const float4* x4n = reinterpret_cast<const float4*>(x + (P.off + tile_of(nidx) * (long long)(TS * D))) + tid;
+                const long long Bn = P.off + tile_of(nidx) * (long long)(TS * D);
 #pragma unroll
-                for (int k = 0; k < NPRE; ++k) pre[k] = __ldcs(x4n + k * PT_THREADS);
+                for (int k = 0; k < NPRE; ++k) pre[k] = ld_pair(Bn, k);
             }
         }
 
@@ -251,7 +276,27 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         }
 
         const long long mbase = m0 + (long long)tid * PT_R;     // output index of acc[0]
-        if constexpr (!DISC) {
+        if constexpr (REAL) {
+            // ---- store: lane 0 -> outputs mbase + r, lane 1 -> outputs mbase + PT_TO + r
+            float* y = reinterpret_cast<float*>(yv);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const long long mb = mbase + half * PT_TO;
+                float v[PT_R];
+#pragma unroll
+                for (int r = 0; r < PT_R; ++r) v[r] = half ? acc[r].y : acc[r].x;
+                if (mb + PT_R <= n_out && ((reinterpret_cast<uintptr_t>(y + mb) & 15) == 0)) {
+#pragma unroll
+                    for (int r = 0; r < PT_R; r += 4)
+                        __stcs(reinterpret_cast<float4*>(y + mb + r), make_float4(v[r], v[r + 1], v[r + 2], v[r + 3]));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < PT_R; ++r)
+                        if (mb + r < n_out) y[mb + r] = v[r];
+                }
+            }
+            __syncthreads();                               // shared tile is reused by the next iteration
+        } else if constexpr (!DISC) {
             // ---- store: 8 consecutive complex outputs per thread
             float2* y = reinterpret_cast<float2*>(yv);
             if (mbase + PT_R <= n_out && ((reinterpret_cast<uintptr_t>(y + mbase) & 15) == 0)) {
@@ -315,16 +360,19 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
     }
 }
 
-template <int D, int Q, bool ROT, bool DISC>
+template <int D, int Q, bool ROT, bool DISC, bool REAL = false>
 int launch_shape(PolyParams P, const float* hr_base, const float2* x, const float2* hist, long long n,
                  void* y, long long first, long long n_out, const float2* prev_in, float2* prev_out, float inv_gain,
                  cudaStream_t s) {
     using S = PolyShape<D, Q>;
     static_assert(S::T <= PT_MAXTAPS, "taps table too small");
-    static bool configured = false;
-    static int ctas_per_sm = 1;
-    auto kern_i = polyphase_crcf_kernel<D, Q, ROT, DISC, false>;
-    auto kern_e = polyphase_crcf_kernel<D, Q, ROT, DISC, true>;
+    // function attributes are per device: a process that drives several GPUs configures each once
+    static bool configured_dev[LRB_MAX_DEVICES] = {false};
+    static int ctas_dev[LRB_MAX_DEVICES] = {0};
+    bool& configured = configured_dev[ctx().device & (LRB_MAX_DEVICES - 1)];
+    int& ctas_per_sm = ctas_dev[ctx().device & (LRB_MAX_DEVICES - 1)];
+    auto kern_i = polyphase_crcf_kernel<D, Q, ROT, DISC, false, REAL>;
+    auto kern_e = polyphase_crcf_kernel<D, Q, ROT, DISC, true, REAL>;
     if (!configured) {
         LRB_CHECK(cudaFuncSetAttribute(kern_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         LRB_CHECK(cudaFuncSetAttribute(kern_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
@@ -332,7 +380,7 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = true;
     }
-    constexpr int TS = TileStride<DISC>::TS;
+    constexpr int TS = REAL ? 2 * PT_TO : TileStride<DISC>::TS;
     // B(tile) = first + m0*D - (Q*D - 1) - shift, m0 = tile*TS - (DISC ? 1 : 0); shift in {0,1} makes it even
     long long off = first - (DISC ? D : 0) - (long long)(Q * D - 1);
     const int shift = (int)(((off % 2) + 2) % 2);
@@ -346,10 +394,10 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
     const long long tiles = (n_out + TS - 1) / TS;
     // interior tiles: every staged sample B(t) .. B(t)+LOADED-1 inside [0, n) and x 16-byte aligned
     long long t_lo = 0, t_hi = 0;
-    if ((reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    if ((reinterpret_cast<uintptr_t>(x) & (REAL ? 7 : 15)) == 0) {
         const long long step = (long long)TS * D;
         t_lo = off >= 0 ? 0 : (-off + step - 1) / step;
-        const long long lim = n - (long long)S::LOADED - off;
+        const long long lim = n - (long long)S::LOADED - off - (REAL ? (long long)PT_TO * D : 0);
         t_hi = lim < 0 ? 0 : lim / step + 1;
         if (t_hi > tiles) t_hi = tiles;
         if (t_lo > t_hi) t_lo = t_hi;
@@ -380,6 +428,7 @@ struct PolyTaps {
     uint64_t turns_fix;
     float2 step[PT_MAXIT];       // per-staging-iteration phasor advance (see PolyParams)
     bool rotates = false;        // a translator is fused
+    bool real_data = false;      // float32 stream (REAL kernel variant)
 };
 
 static int shape_q(int M, int D, bool rotates) {
@@ -394,12 +443,20 @@ static int shape_q(int M, int D, bool rotates) {
     return 0;
 }
 
-PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table) {
-    int Q = shape_q(M, D, phasor_table);
+// real input / real taps decimators (REAL variant): the chain's audio stage Lowpass(128) * de-emphasis(6) -> /5 is
+// 133 taps, Q = 27; the plain DecimatorBlock on Float32 (composites/decimator.lua:34-41) with 128 taps is Q = 26.
+static int shape_q_real(int M, int D) {
+    if (D == 5 && M > 130 && M <= 135) return 27;
+    return 0;
+}
+
+PolyTaps* polyphase_prepare(const float* taps, int M, int D, double turns_per_sample, bool phasor_table, bool real_data) {
+    int Q = real_data ? shape_q_real(M, D) : shape_q(M, D, phasor_table);
     if (!Q) return nullptr;
     PolyTaps* p = new (std::nothrow) PolyTaps();
     if (!p) return nullptr;
     p->M = M; p->D = D; p->Q = Q;
+    p->real_data = real_data;
     // hr[i'] multiplies X[c - (Q*D-1) + i']  =>  hr[i'] = h[Q*D-1-i'] (zero for tap index >= M)
     for (int i = 0; i < PT_MAXTAPS; ++i) {
         int k = Q * D - 1 - i;
@@ -452,9 +509,20 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
     std::memcpy(P.step, p->step, sizeof(P.step));
     P.g0 = g0;
     P.M = p->M;
+    if (p->real_data) {
+        if (rot || disc) { set_error("polyphase: the real-stream kernel has no translator / discriminator"); return -1; }
+        if (p->D == 5 && p->Q == 27)
+            return launch_shape<5, 27, false, false, true>(P, p->hr, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);
+        return 0;
+    }
     LRB_SHAPE_PLAIN(1, 16) LRB_SHAPE_PLAIN(1, 32)
     LRB_SHAPE_FULL(5, 26)
     return 0;
+}
+
+int launch_polyphase_rrrf(const PolyTaps* p, const float* x, const float* hist, long long n, float* y,
+                          long long first, long long n_out, cudaStream_t s) {
+    return launch_polyphase_any(p, (const float2*)x, (const float2*)hist, n, y, first, n_out, false, false, 0, nullptr, nullptr, 0.f, s);
 }
 
 int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist, long long n, float2* y,

@@ -1,0 +1,126 @@
+"""Round-2 GPU parity: the graph rewrites and kernels added after round 1.
+
+  * audio tail  Lowpass(128) -> FMDeemphasis -> Downsampler(5)  rewritten by the noble identity into ONE 133-tap
+    decimating real FIR + a pole c^5 at the output rate (graph.cu) -- against the oracle's block-by-block chain;
+  * the fused Tuner -> FrequencyDiscriminator stage checked DIRECTLY at the reference's own 1e-6 absolute
+    (tests/blocks/signal/frequencydiscriminator_spec.lua epsilon), not after the audio low-pass has averaged it;
+  * the real-stream polyphase decimator through the C ABI with ragged calls.
+
+Tolerance unless stated: |got - ref| <= 1e-5 * max(1, ||ref||_inf) (north_star)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import luaradio_b200 as radio
+from luaradio_b200 import _lib
+from oracle import lr_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def close(got, ref, rel=1e-5, absolute=None):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, "length %s != %s" % (got.shape, ref.shape)
+    if ref.size == 0:
+        return
+    tol = absolute if absolute is not None else rel * max(1.0, float(np.max(np.abs(ref))))
+    err = float(np.max(np.abs(got.astype(np.complex128) - ref.astype(np.complex128))))
+    assert err <= tol, "max abs err %.3g > %.3g" % (err, tol)
+
+
+def run_graph(blocks, x, rate, chunk, fuse=True):
+    src, snk = radio.ArraySource(x, rate, chunk), radio.ArraySink()
+    top = radio.CompositeBlock()
+    top.connect(src, *blocks, snk)
+    top.run(False, fuse=fuse)
+    return snk.result(), top
+
+
+def audio_tail_blocks():
+    return [radio.LowpassFilterBlock(128, 15e3), radio.FMDeemphasisFilterBlock(75e-6), radio.DownsamplerBlock(5)]
+
+
+def audio_tail_oracle(rate):
+    b, a = O.fm_deemphasis_taps(75e-6, rate)
+    return O.Chain(O.lowpass_filter(128, 15e3, rate, False), O.IIRFilterFast(b, a, False), O.Downsampler(5))
+
+
+@pytest.mark.parametrize("chunk", [1 << 22, 100003, 4099, 7])
+def test_audio_tail_noble_identity(chunk):
+    """examples/rtlsdr_wbfm_mono.lua:15-18 on a real stream at 220.5 kHz: three blocks -> two stages, and the stream is
+    the same whatever the vector size (the decimation phase, the 132-sample history and the pole state are carried)."""
+    rate = 220500.0
+    n = 400000 if chunk > 100 else 30000
+    rng = np.random.default_rng(11)
+    t = np.arange(n) / rate
+    x = (0.4 * np.sin(2 * np.pi * 1000 * t) + 0.3 * np.sin(2 * np.pi * 9000 * t) + 0.2 * rng.uniform(-1, 1, n)).astype(np.float32)
+    got, top = run_graph(audio_tail_blocks(), x, rate, chunk)
+    desc = top.describe_gpu_graph()
+    assert desc == "fir*iir1_rrrf(133,/5)[fused x3] | pole_rrrf", desc
+    ref = audio_tail_oracle(rate).process(x)
+    close(got, ref)
+    # chunked == whole to float32 rounding (the streaming state is exact, only summation grouping at tile edges differs)
+    whole, _ = run_graph(audio_tail_blocks(), x, rate, 1 << 24)
+    close(got, whole, absolute=2e-6)
+    # and the unfused graph (three kernels, the reference's dataflow) agrees too
+    unf, top2 = run_graph(audio_tail_blocks(), x, rate, chunk if chunk > 100 else 1 << 20, fuse=False)
+    assert top2.describe_gpu_graph().count("|") == 2
+    close(unf, ref)
+
+
+def test_audio_tail_other_shapes_keep_the_old_fusion():
+    """A shape the real polyphase kernel does not have (64 taps, /4) must still be correct: FIR | IIR+down."""
+    rate = 48000.0
+    rng = np.random.default_rng(12)
+    x = rng.uniform(-1, 1, 200000).astype(np.float32)
+    blocks = [radio.LowpassFilterBlock(64, 5e3), radio.SinglepoleLowpassFilterBlock(2e3), radio.DownsamplerBlock(4)]
+    got, top = run_graph(blocks, x, rate, 50000)
+    b, a = O.singlepole_lowpass_taps(2e3, rate)
+    ref = O.Chain(O.lowpass_filter(64, 5e3, rate, False), O.IIRFilterFast(b, a, False), O.Downsampler(4)).process(x)
+    close(got, ref)
+
+
+@pytest.mark.parametrize("chunk", [1 << 22, 65536, 12345])
+def test_tuner_discriminator_direct_1e6(chunk):
+    """Tuner(-250e3, 200e3, 5) -> FrequencyDiscriminator(1.25) -> sink: the fused tuner+discriminator stage (packed
+    atan2, tile phasor skipped) at the reference spec's 1e-6 absolute tolerance on a strong FM signal."""
+    n = 500000
+    x = O.synth_fm_iq(0, n)
+    got, top = run_graph([radio.TunerBlock(-250e3, 200e3, 5), radio.FrequencyDiscriminatorBlock(1.25)], x, 1102500.0, chunk)
+    assert top.describe_gpu_graph().startswith("tuner+discrim(128,/5)"), top.describe_gpu_graph()
+    ref = O.Chain(O.tuner(-250e3, 200e3, 5, 1102500.0), O.FrequencyDiscriminator(1.25)).process(x)
+    assert got.shape == ref.shape
+    # the first 26 outputs come from the filter's start-up transient (|y| ~ 1e-4: the angle of a near-zero phasor is
+    # ill-conditioned -- the reference's own vectors avoid it by construction); from there on: 1e-6 absolute
+    err = np.abs(got[26:] - ref[26:])
+    assert float(err.max()) <= 1e-6, "max abs err %.3g" % float(err.max())
+    close(got[:26], ref[:26], absolute=2e-5)
+
+
+@pytest.mark.parametrize("M,D", [(133, 5), (131, 5), (135, 5)])
+def test_real_polyphase_decimator_c_abi(M, D):
+    """lrb200_fir_create_rrrf(taps, M, decim=5): the real-stream polyphase kernel through HOST-mode calls of ragged
+    length (one sample up to several tiles), against FIR -> Downsampler of the oracle."""
+    rng = np.random.default_rng(M)
+    n = 300000
+    taps = O.f32_taps(O.firwin_lowpass(M, 1.0 / D))
+    x = rng.uniform(-1, 1, n).astype(np.float32)
+    lib = _lib.require_device()
+    h = _lib.check_handle(lib.lrb200_fir_create_rrrf(taps.ctypes.data, M, D, _lib.LRB200_HOST), "fir")
+    assert lib.lrb200_fir_get_algorithm(h) == _lib.FIR_DIRECT
+    outs, i = [], 0
+    sizes = [1, 2, 3, 4, 5, 17, 4096, 20481, 100000, 1, 7, 50000]
+    k = 0
+    while i < n:
+        m = min(n - i, sizes[k % len(sizes)])
+        k += 1
+        seg = np.ascontiguousarray(x[i:i + m])
+        out = np.zeros(lib.lrb200_block_max_output(h, m), np.float32)
+        no = ctypes.c_size_t()
+        _lib.check(lib.lrb200_fir_execute(h, seg.ctypes.data, m, out.ctypes.data, ctypes.byref(no)))
+        outs.append(out[:no.value])
+        i += m
+    lib.lrb200_fir_destroy(h)
+    ref = O.Chain(O.FIRFilter(taps, False), O.Downsampler(D)).process(x)
+    close(np.concatenate(outs), ref)
