@@ -52,6 +52,7 @@ typedef struct { float value; } float32_t;
  * platform.libs.X).  lrb200_init is lazy-safe: create functions call it with the current device. */
 int         lrb200_init(int device);                 /* 0 ok, <0 error (no device, wrong arch)   */
 int         lrb200_device_count(void);               /* 0 when no CUDA device is usable          */
+int         lrb200_current_device(void);             /* device of the last successful lrb200_init, -1 before */
 const char* lrb200_last_error(void);                 /* thread-local, never NULL                 */
 const char* lrb200_version(void);
 int         lrb200_set_stream(void* cuda_stream);    /* use the caller's cudaStream_t (NULL = own) */
@@ -199,9 +200,31 @@ int    lrb200_graph_append(lrb200_graph_t* g, lrb200_block_t* q);   /* connect q
 int    lrb200_graph_commit(lrb200_graph_t* g, int fuse);            /* fuse != 0: apply kernel fusion   */
 int    lrb200_graph_execute(lrb200_graph_t* g, const void* x, size_t n, void* y, size_t* n_out);        /* HOST in/out   */
 int    lrb200_graph_execute_device(lrb200_graph_t* g, const void* dx, size_t n, void* dy, size_t* n_out); /* DEVICE in/out, async */
-size_t lrb200_graph_max_output(const lrb200_graph_t* g, size_t n);
+size_t lrb200_graph_max_output(const lrb200_graph_t* g, size_t n);  /* room `y` of the next execute(n) must have  */
+/* Super-chunk mode for the reference's per-vector regime (vectors of <= 131072 samples, typically 8192:
+ * radio/core/pipe.lua:73, radio/blocks/sources/zero.lua:30).  With samples > 0, lrb200_graph_execute packs the host
+ * vectors into pinned slots of `samples` input samples; a full slot is uploaded and processed asynchronously while the
+ * next one fills, and execute hands back (possibly zero) output samples of slots completed earlier -- a block may
+ * return any number of samples per process() call (docs/5.architecture.md:36-47; FIRFilterBlock:process_fft itself
+ * emits whole blocks only, firfilter.lua:362).  lrb200_graph_flush pushes the partial slot through and drains
+ * (call it at end of stream, where the reference's run loop sees EOF: radio/core/block.lua:588).  samples == 0
+ * switches back to synchronous calls. */
+int    lrb200_graph_set_superchunk(lrb200_graph_t* g, size_t samples);
+int    lrb200_graph_flush(lrb200_graph_t* g, void* y, size_t* n_out);
 int    lrb200_graph_reset(lrb200_graph_t* g);
 int    lrb200_graph_seek(lrb200_graph_t* g, uint64_t sample_index);
+/* Time-chunk sharding of one stream over several GPUs / processes (the reference has no counterpart --
+ * it parallelises by block, radio/core/composite.lua:568-636).  lrb200_graph_halo: input samples of left context a
+ * cold start needs before the outputs equal the streaming ones to float32 resolution (FIR histories, single-pole
+ * decay to 1e-12, one discriminator sample), rounded up to whole output periods; < 0 if some stage has unbounded
+ * memory.  lrb200_graph_execute_shard runs one chunk: dx -> DEVICE [halo samples of the left neighbour | n samples of
+ * this chunk], the chunk starting at global input index `start`; the chunk's kernels start at once, only a head piece
+ * of 2*halo samples (run by g_head, a second identical graph, on its own stream) waits for `halo_ready_event`
+ * (a cudaEvent_t recorded after the neighbour's samples landed, or NULL), so the exchange overlaps the compute.
+ * Asynchronous on the library stream; dy receives exactly the outputs of a single-device run for this chunk. */
+long long lrb200_graph_halo(lrb200_graph_t* g);
+int    lrb200_graph_execute_shard(lrb200_graph_t* g, lrb200_graph_t* g_head, const void* dx, size_t halo, size_t n,
+                                  uint64_t start, void* dy, size_t* n_out, void* halo_ready_event);
 int    lrb200_graph_num_stages(const lrb200_graph_t* g);            /* kernels stages after fusion */
 const char* lrb200_graph_describe(const lrb200_graph_t* g);         /* e.g. "tuner(128,/5) | discrim+fir(128) | iir1+down(/5)" */
 const char* lrb200_graph_stage_name(const lrb200_graph_t* g, int stage);

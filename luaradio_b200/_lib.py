@@ -6,7 +6,7 @@ missing, or no CUDA device is usable, every block's initialize() raises.
 """
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_size_t, c_uint, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_uint, c_uint32, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LRB200_LIB", os.path.join(_HERE, "libluaradio_b200.so"))   # override: A/B-testing kernel builds
@@ -21,6 +21,7 @@ _PROTOS = {
     # name: (restype, argtypes)
     "lrb200_init": (c_int, [c_int]),
     "lrb200_device_count": (c_int, []),
+    "lrb200_current_device": (c_int, []),
     "lrb200_last_error": (c_char_p, []),
     "lrb200_version": (c_char_p, []),
     "lrb200_set_stream": (c_int, [c_void_p]),
@@ -70,6 +71,10 @@ _PROTOS = {
     "lrb200_graph_execute": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "lrb200_graph_execute_device": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "lrb200_graph_max_output": (c_size_t, [c_void_p, c_size_t]),
+    "lrb200_graph_set_superchunk": (c_int, [c_void_p, c_size_t]),
+    "lrb200_graph_flush": (c_int, [c_void_p, c_void_p, POINTER(c_size_t)]),
+    "lrb200_graph_halo": (c_longlong, [c_void_p]),
+    "lrb200_graph_execute_shard": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_uint64, c_void_p, POINTER(c_size_t), c_void_p]),
     "lrb200_graph_reset": (c_int, [c_void_p]),
     "lrb200_graph_seek": (c_int, [c_void_p, c_uint64]),
     "lrb200_graph_num_stages": (c_int, [c_void_p]),
@@ -121,8 +126,15 @@ def check_handle(h, what):
     return h
 
 
-def require_device(device=0):
-    """Initialise the library on `device`; raises LibraryError (loudly) when no GPU is usable."""
+def require_device(device=None):
+    """Initialise the library; raises LibraryError (loudly) when no GPU is usable.  Without an argument the device the
+    process already selected (an earlier require_device(n), e.g. one rank per GPU) is kept -- re-initialising on device 0
+    would move the library stream and leave every existing handle on the wrong GPU; an explicit `device` switches."""
     lib = load()
+    if device is None:
+        cur = lib.lrb200_current_device()
+        if cur >= 0:
+            return lib
+        device = 0
     check(lib.lrb200_init(device), "lrb200_init(%d)" % device)
     return lib

@@ -15,8 +15,6 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libluaradio_b200.so")
 SOURCES = ["capi.cu", "graph.cu", "fir_direct.cu", "fir_fft.cu", "tuner.cu", "elementwise.cu", "iir.cu", "synth.cu", "iqconv.cu", "resample.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--use_fast_math=false".replace("=false", "") if False else "-Xcompiler", "-fvisibility=hidden"]
 # --split-compile 0: the fully unrolled tuner / FFT kernels are dozens of large kernels per file; let ptxas use every core
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--split-compile", "0"]
 FLAGS += os.environ.get("LRB200_NVCC_EXTRA", "").split()
@@ -59,8 +57,10 @@ def build(force=False, verbose=False):
                     sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed for " + cmd[-3])
-    if jobs or force or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+    if jobs or force or _stale(LIB, objs + [os.path.join(CSRC, "exports.map")]):
+        # only the C ABI (include/lrb200.h) is exported; the internal lrb:: symbols stay local
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + \
+              ["-Xlinker", "--version-script=" + os.path.join(CSRC, "exports.map"), "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

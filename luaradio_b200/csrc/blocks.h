@@ -28,6 +28,11 @@ struct Block {
     virtual int seek(uint64_t idx) { consumed = idx; return 0; }
     // number of outputs this block has produced once `idx` inputs are consumed (for graph seek)
     virtual uint64_t outputs_before(uint64_t idx) const { return idx; }
+    // time-chunk sharding: how many INPUT samples of left context a cold start needs before this block's
+    // outputs equal the streaming ones to float32 resolution (FIR history, IIR decay to 1e-12, ...); < 0 = unbounded
+    virtual long long memory_in() const { return 0; }
+    // output rate / input rate = up / down
+    virtual void rate(unsigned* up, unsigned* down) const { *up = 1; *down = 1; }
     int execute(const void* x, size_t n, void* y, size_t* n_out);
     static int reserve(void** p, size_t* cap, size_t bytes);
 };
@@ -50,6 +55,12 @@ struct FirBlock : Block {
     FirFast* fast = nullptr;
     PolyTaps* poly = nullptr;
     std::string label;                // owns `name` when a graph rewrite renames the block
+    // output-rate pole fused behind a real polyphase decimator (graph rewrite of FIR -> IIR1 -> Downsampler)
+    bool has_pole = false;
+    float pole_c = 0.f;
+    void* d_pole[2] = {nullptr, nullptr};
+    int pcur = 0;
+    int set_pole(float c);
 
     FirBlock(FirKind k, const void* taps_host, unsigned ntaps, unsigned decim, bool dev);
     void set_rotation(double turns_per_sample) { rotate = true; rot_turns = turns_per_sample; rot_fix = turns_to_fix(turns_per_sample); }
@@ -60,6 +71,8 @@ struct FirBlock : Block {
     void reset_host() override;
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+    long long memory_in() const override;
+    void rate(unsigned* up, unsigned* down) const override { *up = 1; *down = (unsigned)D; }
     // fast paths (fir_fft.cu): fast_run returns 1 if it handled the call, 0 to fall back, <0 on error
     int fast_init();
     void fast_free();
@@ -84,6 +97,7 @@ struct DiscrimBlock : Block {
     void reset_host() override;
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+    long long memory_in() const override { return 1; }
 };
 
 struct DownsampleBlock : Block {
@@ -92,6 +106,7 @@ struct DownsampleBlock : Block {
     size_t max_output(size_t n) const override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+    void rate(unsigned* up, unsigned* down) const override { *up = 1; *down = (unsigned)D; }
 };
 
 struct IirBlock : Block {
@@ -112,6 +127,8 @@ struct IirBlock : Block {
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+    long long memory_in() const override;
+    void rate(unsigned* up, unsigned* down) const override { *up = 1; *down = (unsigned)D; }
 };
 
 // IIRFilterBlock of any order (na > 2): direct form I, time-parallel chunks with a measured warm-up
@@ -129,6 +146,7 @@ struct IirGeneralBlock : Block {
     void reset_host() override;
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+    long long memory_in() const override { return warm < 0 ? -1 : warm + nb; }
 };
 
 struct C2fBlock : Block {
@@ -150,6 +168,7 @@ struct UpsampleBlock : Block {        // UpsamplerBlock
     UpsampleBlock(unsigned factor, unsigned elem, bool dev);
     size_t max_output(size_t n) const override { return n * (size_t)L; }
     uint64_t outputs_before(uint64_t idx) const override { return idx * (uint64_t)L; }
+    void rate(unsigned* up, unsigned* down) const override { *up = (unsigned)L; *down = 1; }
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
 };
 
@@ -172,6 +191,8 @@ struct InterpFirBlock : Block {       // [MultiplyConstant ->] Upsampler -> FIR(
     void reset_host() override { consumed = 0; cur = 0; }
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override;
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override;
+    long long memory_in() const override { return Hn + 1; }
+    void rate(unsigned* up, unsigned* down) const override { *up = (unsigned)L; *down = (unsigned)D; }
 };
 
 }  // namespace lrb
@@ -189,8 +210,11 @@ int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist
                           long long first, long long n_out, bool rotate, uint64_t turns_fix, uint64_t g0,
                           cudaStream_t s);
 // real input, real taps, decimating (x / hist / y are float32)
+// z_in != nullptr additionally fuses the output-rate pole z[m] = pole_c z[m-1] + w[m] (state carried in z_in -> z_out)
 int launch_polyphase_rrrf(const PolyTaps* p, const float* x, const float* hist, long long n, float* y,
-                          long long first, long long n_out, cudaStream_t s);
+                          long long first, long long n_out, cudaStream_t s, float pole_c = 0.f,
+                          const float* z_in = nullptr, float* z_out = nullptr);
+bool polyphase_pole_ok(float c);     // the pole's memory fits the kernel's warm-up
 // tuner.cu: fused FrequencyTranslator -> FIR(crcf) -> Downsampler; returns nullptr (with the error set) on failure
 // iqconv.cu: IQFileSource sample format -> ComplexFloat32 (nullptr + error for an unknown format)
 Block* make_iqconv(const char* format, bool dev);

@@ -145,7 +145,19 @@ int FirBlock::init() {
     return fast_init();
 }
 
+int FirBlock::set_pole(float c) {
+    for (int i = 0; i < 2; ++i) {
+        LRB_CHECK(cudaMalloc(&d_pole[i], sizeof(float)));
+        LRB_CHECK(cudaMemset(d_pole[i], 0, sizeof(float)));
+    }
+    has_pole = true;
+    pole_c = c;
+    return 0;
+}
+
 FirBlock::~FirBlock() {
+    cudaFree(d_pole[0]);
+    cudaFree(d_pole[1]);
     cudaFree(d_taps);
     cudaFree(d_hist[0]);
     cudaFree(d_hist[1]);
@@ -154,11 +166,33 @@ FirBlock::~FirBlock() {
 
 size_t FirBlock::max_output(size_t n) const { return D == 1 ? n : n / D + 1; }
 
-void FirBlock::reset_host() { consumed = 0; cur = 0; }
+static long long decay_samples(double c) {        // samples until |c|^k < 1e-12; < 0 if it never gets there
+    const double a = std::fabs(c);
+    if (a == 0.0) return 0;
+    if (a >= 1.0) return -1;
+    return (long long)std::ceil(std::log(1e-12) / std::log(a)) + 1;
+}
+
+long long FirBlock::memory_in() const {
+    long long m = M - 1;
+    if (has_pole) {
+        const long long w = decay_samples((double)pole_c);
+        if (w < 0) return -1;
+        m += w * D;
+    }
+    return m;
+}
+long long IirBlock::memory_in() const {
+    const long long w = decay_samples((double)c);
+    return w < 0 ? -1 : w + nb;
+}
+
+void FirBlock::reset_host() { consumed = 0; cur = 0; pcur = 0; }
 void FirBlock::state_buffers(std::vector<std::pair<void*, size_t>>& segs) {
     const size_t hb = (size_t)(M > 1 ? M - 1 : 1) * in_size;
     segs.push_back({d_hist[0], hb});
     segs.push_back({d_hist[1], hb});
+    if (has_pole) { segs.push_back({d_pole[0], sizeof(float)}); segs.push_back({d_pole[1], sizeof(float)}); }
 }
 
 int FirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) {
@@ -167,9 +201,10 @@ int FirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_
     *n_out = (size_t)no;
     if (n == 0) return 0;
     // the history for the next call depends only on x and the old history: side stream, concurrent with the filter
+    // (short calls -- the reference's 8192-sample vectors -- are launch-latency bound: no fork/join events for them)
     cudaStream_t side = s;
     if (M > 1) {
-        side = side_fork(s);
+        if (n >= SIDE_STREAM_MIN) side = side_fork(s);
         if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, (int)in_size, side) != 0) return -1;
     }
     int rc = fast_run(dx, n, dy, first, no, s);
@@ -177,6 +212,7 @@ int FirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_
     side_join(s, side);
     if (rc < 0) return -1;
     if (M > 1) cur ^= 1;
+    if (has_pole && no > 0) pcur ^= 1;
     consumed += n;
     return 0;
 }
@@ -408,9 +444,16 @@ int lrb200_init(int device) {
         return -1;
     }
     if (g_ctx.device != device) {
+        // switching devices: the library stream, the side stream and its events belong to the old device.  Handles
+        // created on the old device keep their buffers there and must not be used while another device is current.
         if (g_ctx.own_stream && g_ctx.stream) cudaStreamDestroy(g_ctx.stream);
         g_ctx.stream = nullptr;
         g_ctx.own_stream = false;
+        if (g_ctx.side) cudaStreamDestroy(g_ctx.side);
+        if (g_ctx.ev_fork) cudaEventDestroy(g_ctx.ev_fork);
+        if (g_ctx.ev_join) cudaEventDestroy(g_ctx.ev_join);
+        g_ctx.side = nullptr;
+        g_ctx.ev_fork = g_ctx.ev_join = nullptr;
     }
     g_ctx.device = device;
     g_ctx.sm_count = prop.multiProcessorCount;
@@ -426,6 +469,8 @@ int lrb200_device_count(void) {
     if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
     return count;
 }
+
+int lrb200_current_device(void) { return g_ctx.device; }
 
 const char* lrb200_last_error(void) { return g_err; }
 const char* lrb200_version(void) { return "luaradio_b200 0.1.0 (sm_100a)"; }

@@ -43,6 +43,7 @@ inline uint64_t turns_to_fix(double turns) {
 
 // fork: returns a stream that has waited for everything enqueued on `s` so far (or `s` itself if unavailable);
 // join: makes `s` wait for the side stream.  Used as  side = side_fork(s); edge<<<..., side>>>; main<<<..., s>>>; side_join(s).
+constexpr size_t SIDE_STREAM_MIN = (size_t)1 << 18;   // below this many samples the few-CTA kernels stay on the main stream
 cudaStream_t side_fork(cudaStream_t s);
 void side_join(cudaStream_t s, cudaStream_t side);
 

@@ -635,7 +635,9 @@ int FirBlock::set_algorithm(int a) {
 
 int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long long n_out, cudaStream_t s) {
     if (poly && algo != LRB200_FIR_FFT && kind == FIR_RRRF)
-        return launch_polyphase_rrrf(poly, (const float*)dx, (const float*)d_hist[cur], (long long)n, (float*)dy, first, n_out, s);
+        return launch_polyphase_rrrf(poly, (const float*)dx, (const float*)d_hist[cur], (long long)n, (float*)dy, first, n_out, s,
+                                     pole_c, has_pole ? (const float*)d_pole[pcur] : nullptr, has_pole ? (float*)d_pole[pcur ^ 1] : nullptr);
+    if (has_pole) { set_error("fir: the fused output-rate pole needs the real polyphase kernel"); return -1; }
     if (poly && algo != LRB200_FIR_FFT)
         return launch_polyphase_crcf(poly, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, (float2*)dy,
                                      first, n_out, false, 0, consumed, s);

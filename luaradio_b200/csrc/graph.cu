@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "blocks.h"
 
+#include <cmath>
+#include <cstring>
 #include <new>
 #include <string>
 #include <vector>
@@ -33,6 +35,23 @@ struct Graph {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     size_t host_chunk = (size_t)1 << 23;   // input samples per pipelined chunk
     std::string desc;
+    // super-chunk mode (SURVEY.md 8e "streaming mode"): small host vectors are packed into pinned slots of `sc` samples;
+    // a full slot is processed asynchronously while the next one fills, and its outputs are handed back when that next
+    // slot is submitted (or at flush) -- the per-vector cost is one host memcpy instead of copies + launches + a sync
+    size_t sc = 0;
+    char* sc_hin[2] = {nullptr, nullptr};
+    char* sc_hout[2] = {nullptr, nullptr};
+    void* sc_din[2] = {nullptr, nullptr};
+    void* sc_dout[2] = {nullptr, nullptr};
+    cudaEvent_t sc_done[2] = {nullptr, nullptr};
+    bool sc_pending[2] = {false, false};
+    size_t sc_nout[2] = {0, 0};
+    size_t sc_fill = 0, sc_outcap = 0;
+    int sc_cur = 0;
+    // time-chunk sharding: output of the head piece (execute_shard) and the stream / events it runs on
+    void* head_out = nullptr; size_t head_out_cap = 0;
+    cudaStream_t s_head = nullptr;
+    cudaEvent_t ev_head = nullptr, ev_main = nullptr;
     // optional per-stage timing
     bool timing = false;
     std::vector<std::vector<cudaEvent_t>> tev;   // per stage: [start0, stop0, start1, stop1, ...]
@@ -57,6 +76,23 @@ struct Graph {
         }
         if (s_h2d) cudaStreamDestroy(s_h2d);
         if (s_d2h) cudaStreamDestroy(s_d2h);
+        free_superchunk();
+        cudaFree(head_out);
+        if (s_head) cudaStreamDestroy(s_head);
+        if (ev_head) cudaEventDestroy(ev_head);
+        if (ev_main) cudaEventDestroy(ev_main);
+    }
+
+    void free_superchunk() {
+        for (int i = 0; i < 2; ++i) {
+            if (sc_hin[i]) cudaFreeHost(sc_hin[i]);
+            if (sc_hout[i]) cudaFreeHost(sc_hout[i]);
+            cudaFree(sc_din[i]); cudaFree(sc_dout[i]);
+            if (sc_done[i]) cudaEventDestroy(sc_done[i]);
+            sc_hin[i] = sc_hout[i] = nullptr; sc_din[i] = sc_dout[i] = nullptr; sc_done[i] = nullptr;
+            sc_pending[i] = false; sc_nout[i] = 0;
+        }
+        sc = 0; sc_fill = 0; sc_cur = 0;
     }
 
     size_t max_output(size_t n) const {
@@ -150,7 +186,14 @@ struct Graph {
                         if (!nf) { set_error("out of memory"); return -1; }
                         nf->set_algorithm(fir->algo);
                         if (nf->init() != 0) { delete nf; return -1; }
-                        if (nf->poly) {      // only worth it when the polyphase kernel has this shape
+                        if (nf->poly && nf->algo != LRB200_FIR_FFT && polyphase_pole_ok((float)cp)) {
+                            // the pole's memory (|c^D|^64 <= 1e-8) fits the kernel's own warm-up: ONE stage
+                            if (nf->set_pole((float)cp) != 0) { delete nf; return -1; }
+                            nf->label = "fir*iir1_rrrf(" + std::to_string(Mc) + ",/" + std::to_string(Dd) + ")+pole";
+                            nf->name = nf->label.c_str();
+                            fused.push_back(nf);
+                            st = nf; used = 3;
+                        } else if (nf->poly) {      // only worth it when the polyphase kernel has this shape
                             const float one = 1.0f, a2[2] = {1.0f, (float)(-cp)};     // cp == c^D
                             IirBlock* ni = new (std::nothrow) IirBlock(false, &one, 1, a2, 2, true);
                             if (!ni) { delete nf; set_error("out of memory"); return -1; }
@@ -255,9 +298,27 @@ struct Graph {
     int run_host(const void* x, size_t n, void* y, size_t* n_out) {
         if (!committed && commit(1) != 0) return -1;
         if (stages.empty()) { set_error("graph: no blocks"); return -1; }
-        if (ensure_host_pipeline() != 0) return -1;
         cudaStream_t s = ctx().stream;
         const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
+        if (sc) return run_accumulate(x, n, y, n_out);
+        if (n <= host_chunk) {
+            // one chunk (every call of the reference's per-vector regime, pipe.lua:73): copy, kernels and copy back in
+            // order on ONE stream with ONE synchronize -- no cross-stream events, nothing to overlap anyway
+            const size_t mo = max_output(n);
+            if (n * isz > d_in_cap[0] || (mo ? mo : 1) * osz > d_out_cap[0]) {
+                LRB_CHECK(cudaStreamSynchronize(s));
+                if (Block::reserve(&d_in[0], &d_in_cap[0], (n ? n : 1) * isz) != 0) return -1;
+                if (Block::reserve(&d_out[0], &d_out_cap[0], (mo ? mo : 1) * osz) != 0) return -1;
+            }
+            size_t no = 0;
+            if (n) LRB_CHECK(cudaMemcpyAsync(d_in[0], x, n * isz, cudaMemcpyHostToDevice, s));
+            if (run_device(d_in[0], n, d_out[0], &no, s) != 0) return -1;
+            if (no) LRB_CHECK(cudaMemcpyAsync(y, d_out[0], no * osz, cudaMemcpyDeviceToHost, s));
+            LRB_CHECK(cudaStreamSynchronize(s));
+            *n_out = no;
+            return 0;
+        }
+        if (ensure_host_pipeline() != 0) return -1;
         size_t done = 0, produced = 0;
         int it = 0;
         while (done < n) {
@@ -284,14 +345,95 @@ struct Graph {
             done += nc;
             ++it;
         }
-        LRB_CHECK(cudaStreamSynchronize(s_h2d));
-        LRB_CHECK(cudaStreamSynchronize(s));
+        // the last download is behind every upload and every kernel (event chain), so one synchronize drains all three
         LRB_CHECK(cudaStreamSynchronize(s_d2h));
+        LRB_CHECK(cudaStreamSynchronize(s));     // (returns at once; keeps the compute stream's error state observable)
         *n_out = produced;
         return 0;
     }
 
-    int reset() {
+    // ---- super-chunk mode -------------------------------------------------------------------------------------
+    int set_superchunk(size_t samples) {
+        if (!committed && commit(1) != 0) return -1;
+        if (stages.empty()) { set_error("graph: no blocks"); return -1; }
+        if (sc_pending[0] || sc_pending[1] || sc_fill) { set_error("graph: flush before changing the super-chunk size"); return -1; }
+        free_superchunk();
+        if (samples == 0) return 0;
+        const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
+        sc_outcap = max_output(samples) + 1;
+        for (int i = 0; i < 2; ++i) {
+            LRB_CHECK(cudaHostAlloc((void**)&sc_hin[i], samples * isz, cudaHostAllocDefault));
+            LRB_CHECK(cudaHostAlloc((void**)&sc_hout[i], sc_outcap * osz, cudaHostAllocDefault));
+            LRB_CHECK(cudaMalloc(&sc_din[i], samples * isz));
+            LRB_CHECK(cudaMalloc(&sc_dout[i], sc_outcap * osz));
+            LRB_CHECK(cudaEventCreateWithFlags(&sc_done[i], cudaEventDisableTiming));
+        }
+        sc = samples;
+        return 0;
+    }
+    size_t sc_collect(int slot, char* y) {
+        if (!sc_pending[slot]) return 0;
+        if (!cuda_ok(cudaEventSynchronize(sc_done[slot]), "cudaEventSynchronize")) return (size_t)-1;
+        const size_t osz = stages.back()->out_size;
+        if (sc_nout[slot]) memcpy(y, sc_hout[slot], sc_nout[slot] * osz);
+        sc_pending[slot] = false;
+        return sc_nout[slot];
+    }
+    int sc_submit(int slot, size_t count) {
+        cudaStream_t s = ctx().stream;
+        const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
+        size_t no = 0;
+        LRB_CHECK(cudaMemcpyAsync(sc_din[slot], sc_hin[slot], count * isz, cudaMemcpyHostToDevice, s));
+        if (run_device(sc_din[slot], count, sc_dout[slot], &no, s) != 0) return -1;
+        if (no) LRB_CHECK(cudaMemcpyAsync(sc_hout[slot], sc_dout[slot], no * osz, cudaMemcpyDeviceToHost, s));
+        LRB_CHECK(cudaEventRecord(sc_done[slot], s));
+        sc_nout[slot] = no;
+        sc_pending[slot] = true;
+        return 0;
+    }
+    int run_accumulate(const void* x, size_t n, void* y, size_t* n_out) {
+        const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
+        const char* xp = (const char*)x;
+        char* yp = (char*)y;
+        size_t produced = 0;
+        while (n > 0) {
+            const size_t take = n < sc - sc_fill ? n : sc - sc_fill;
+            memcpy(sc_hin[sc_cur] + sc_fill * isz, xp, take * isz);
+            sc_fill += take; xp += take * isz; n -= take;
+            if (sc_fill == sc) {
+                // the other slot was submitted one super-chunk ago: its results are (long) ready
+                const size_t got = sc_collect(sc_cur ^ 1, yp + produced * osz);
+                if (got == (size_t)-1) return -1;
+                produced += got;
+                if (sc_submit(sc_cur, sc) != 0) return -1;
+                sc_cur ^= 1;
+                sc_fill = 0;
+            }
+        }
+        *n_out = produced;
+        return 0;
+    }
+    int flush(void* y, size_t* n_out) {
+        *n_out = 0;
+        if (!sc) return 0;
+        const size_t osz = stages.back()->out_size;
+        char* yp = (char*)y;
+        size_t produced = 0;
+        size_t got = sc_collect(sc_cur ^ 1, yp);
+        if (got == (size_t)-1) return -1;
+        produced += got;
+        if (sc_fill) {
+            if (sc_submit(sc_cur, sc_fill) != 0) return -1;
+            got = sc_collect(sc_cur, yp + produced * osz);
+            if (got == (size_t)-1) return -1;
+            produced += got;
+            sc_fill = 0;
+        }
+        *n_out = produced;
+        return 0;
+    }
+
+    int reset(cudaStream_t s) {
         std::vector<std::pair<void*, size_t>> segs;
         for (Block* b : blocks) { b->reset_host(); b->state_buffers(segs); }
         for (Block* b : fused) { b->reset_host(); b->state_buffers(segs); }
@@ -299,7 +441,84 @@ struct Graph {
         std::vector<void*> ptrs;
         std::vector<size_t> bytes;
         for (auto& sg : segs) { ptrs.push_back(sg.first); bytes.push_back(sg.second); }
-        return launch_zero_segments(ptrs.data(), bytes.data(), (int)ptrs.size(), ctx().stream);
+        return launch_zero_segments(ptrs.data(), bytes.data(), (int)ptrs.size(), s);
+    }
+    int reset() { return reset(ctx().stream); }
+
+    // ---- time-chunk sharding -------------------------------------------------------------------
+    // total rate change in lowest terms: outputs per input = up / down
+    void total_rate(unsigned long long* up, unsigned long long* down) const {
+        unsigned long long u = 1, d = 1;
+        for (Block* b : stages) {
+            unsigned bu, bd;
+            b->rate(&bu, &bd);
+            u *= bu; d *= bd;
+            unsigned long long a = u, c = d;
+            while (c) { unsigned long long t = a % c; a = c; c = t; }
+            u /= a; d /= a;
+        }
+        *up = u; *down = d;
+    }
+    // input samples of left context a cold start needs so that the outputs equal the streaming ones to float32
+    // resolution, rounded up to a whole number of output periods; < 0 when a stage's memory is unbounded
+    long long halo() {
+        if (!committed && commit(1) != 0) return -1;
+        double need = 0.0;                                   // at the input rate of the stage being visited
+        for (size_t k = stages.size(); k-- > 0;) {
+            unsigned bu, bd;
+            stages[k]->rate(&bu, &bd);
+            const long long mem = stages[k]->memory_in();
+            if (mem < 0) { set_error("graph: %s has unbounded memory, the stream cannot be cut", stages[k]->name); return -1; }
+            need = std::ceil(need * (double)bd / (double)bu) + (double)mem + 1.0;
+        }
+        unsigned long long up, down;
+        total_rate(&up, &down);
+        const long long q = (long long)down;                 // input samples per whole output period
+        long long h = (long long)need;
+        h = ((h + q - 1) / q) * q;
+        return h;
+    }
+
+    // One time chunk of a sharded stream.  dx -> [halo samples of the left neighbour | n samples of this chunk], the chunk
+    // starting at global input index `start` (a multiple of the output period, like halo).  The chunk itself is run at
+    // once from a cold state on the compute stream; only a head piece of 2*halo samples -- run by `head` (a second,
+    // identical graph) on its own stream after `halo_ready` -- depends on the neighbour's data, and its last halo/period
+    // outputs replace the chunk's first (cold) ones.  So the neighbour exchange overlaps the chunk's kernels.
+    int run_shard(Graph& head, const void* dx, size_t halo_n, size_t n, uint64_t start, void* dy, size_t* n_out, cudaEvent_t halo_ready) {
+        if (!committed && commit(1) != 0) return -1;
+        cudaStream_t s = ctx().stream;
+        const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
+        unsigned long long up, down;
+        total_rate(&up, &down);
+        if (halo_n % down || start % down) { set_error("graph: halo and start must be multiples of %llu input samples", down); return -1; }
+        if (reset(s) != 0 || seek(start) != 0) return -1;
+        if (run_device((const char*)dx + halo_n * isz, n, dy, n_out, s) != 0) return -1;
+        if (halo_n == 0 || start == 0) return 0;             // the stream's first chunk: nothing to its left
+        if (start < halo_n || n < halo_n) { set_error("graph: chunk shorter than the halo"); return -1; }
+        if (!s_head) {
+            LRB_CHECK(cudaStreamCreateWithFlags(&s_head, cudaStreamNonBlocking));
+            LRB_CHECK(cudaEventCreateWithFlags(&ev_head, cudaEventDisableTiming));
+            LRB_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+        }
+        const size_t ho = (size_t)(halo_n / down * up);      // outputs per halo
+        const size_t cap = (head.max_output(2 * halo_n) + 1) * osz;
+        if (cap > head_out_cap) {
+            LRB_CHECK(cudaStreamSynchronize(s_head));
+            if (Block::reserve(&head_out, &head_out_cap, cap) != 0) return -1;
+        }
+        if (halo_ready) LRB_CHECK(cudaStreamWaitEvent(s_head, halo_ready, 0));
+        // the previous step's splice (on s) read head_out: do not overwrite it before that (ev_main was recorded right
+        // behind that splice; waiting on a never-recorded event is a no-op)
+        LRB_CHECK(cudaStreamWaitEvent(s_head, ev_main, 0));
+        size_t nh = 0;
+        if (head.reset(s_head) != 0 || head.seek(start - halo_n) != 0) return -1;
+        if (head.run_device(dx, 2 * halo_n, head_out, &nh, s_head) != 0) return -1;
+        if (nh != 2 * ho) { set_error("graph: head piece produced %zu outputs, expected %zu", nh, 2 * ho); return -1; }
+        LRB_CHECK(cudaEventRecord(ev_head, s_head));
+        LRB_CHECK(cudaStreamWaitEvent(s, ev_head, 0));
+        LRB_CHECK(cudaMemcpyAsync(dy, (const char*)head_out + ho * osz, ho * osz, cudaMemcpyDeviceToDevice, s));
+        LRB_CHECK(cudaEventRecord(ev_main, s));
+        return 0;
     }
 
     int seek(uint64_t idx) {
@@ -368,7 +587,36 @@ size_t lrb200_graph_max_output(const lrb200_graph_t* g, size_t n) {
     if (!g) return 0;
     lrb200_graph_t* gg = const_cast<lrb200_graph_t*>(g);
     if (!gg->g.committed && gg->g.commit(1) != 0) return 0;
+    // super-chunk mode: one call may hand back the results of the slots completed while n samples were appended
+    if (gg->g.sc) return (n / gg->g.sc + 2) * gg->g.sc_outcap;
     return gg->g.max_output(n);
+}
+
+int lrb200_graph_set_superchunk(lrb200_graph_t* g, size_t samples) {
+    if (!g) { set_error("null graph"); return -1; }
+    return g->g.set_superchunk(samples);
+}
+
+int lrb200_graph_flush(lrb200_graph_t* g, void* y, size_t* n_out) {
+    if (!g) { set_error("null graph"); return -1; }
+    size_t no = 0;
+    int rc = g->g.flush(y, &no);
+    if (n_out) *n_out = no;
+    return rc;
+}
+
+long long lrb200_graph_halo(lrb200_graph_t* g) {
+    if (!g) { set_error("null graph"); return -1; }
+    return g->g.halo();
+}
+
+int lrb200_graph_execute_shard(lrb200_graph_t* g, lrb200_graph_t* g_head, const void* dx, size_t halo, size_t n,
+                               uint64_t start, void* dy, size_t* n_out, void* halo_ready_event) {
+    if (!g || !g_head) { set_error("null graph"); return -1; }
+    size_t no = 0;
+    int rc = g->g.run_shard(g_head->g, dx, halo, n, start, dy, &no, (cudaEvent_t)halo_ready_event);
+    if (n_out) *n_out = no;
+    return rc;
 }
 
 int lrb200_graph_reset(lrb200_graph_t* g) {

@@ -70,7 +70,10 @@ struct PolyParams {
     uint64_t g0;                 // global index of x[0]
     long long off;               // B(tile) = off + tile * TS * D   (even)
     int M;
+    float pole_c;                // POLE: the output-rate pole c (z[m] = c z[m-1] + w[m])
+    float pole_cp[6];            // c^(R * 2^k), k < 5; c^(R * 32)
 };
+constexpr int PT_POLE_WARM = 64; // POLE: outputs of warm-up in front of every run (|c|^64 <= 1e-8 is required by the host)
 
 template <int D, int Q>
 struct PolyShape {
@@ -105,7 +108,13 @@ struct TileStride { static constexpr int TS = DISC ? PT_TO - 2 : PT_TO; };
 // INDEPENDENT real streams: element e of the staged tile is (xr[B + e], xr[B + PT_TO*D + e]), so lane 0 computes the
 // tile's first PT_TO outputs and lane 1 the next PT_TO, and every FFMA2 of the unchanged compute phase is two useful
 // real MACs.  x / hist then point to float32 data.
-template <int D, int Q, bool ROT, bool DISC, bool EDGE, bool REAL = false>
+//
+// POLE (REAL only): a single pole at the OUTPUT rate fused behind the filter, z[m] = c z[m-1] + w[m] (the c^D pole the
+// noble identity leaves of an IIR in front of a Downsampler, graph.cu).  Each lane's run of PT_TO outputs starts with
+// PT_POLE_WARM outputs of warm-up that are scanned but not stored (runs overlap by that much), so a run needs nothing
+// from its predecessor beyond float32 resolution; the stream's very first run takes the carried state instead.  The
+// scan is thread-sequential (R) -> warp Kogge-Stone -> Horner over the 4 warps, both lanes at once on packed registers.
+template <int D, int Q, bool ROT, bool DISC, bool EDGE, bool REAL = false, bool POLE = false>
 __global__ void __launch_bounds__(PT_THREADS, LRB_PT_CTAS)
 polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ hist, long long n,
                       void* __restrict__ yv, long long n_out, const __grid_constant__ PolyParams P,
@@ -113,9 +122,12 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                       const float2* __restrict__ prev_in, float2* __restrict__ prev_out, float inv_gain) {
     using S = PolyShape<D, Q>;
     static_assert(!(REAL && (ROT || DISC)), "the real-stream variant has no translator / discriminator");
-    constexpr int TS = REAL ? 2 * PT_TO : TileStride<DISC>::TS;    // outputs per tile
+    static_assert(REAL || !POLE, "the fused pole exists in the real-stream variant only");
+    constexpr int PW = POLE ? PT_POLE_WARM : 0;                    // warm-up outputs in front of each lane's run
+    constexpr int PAY = PT_TO - PW;                                // outputs a lane's run stores
+    constexpr int TS = REAL ? 2 * PAY : TileStride<DISC>::TS;      // outputs per tile
     constexpr int NPRE = S::ITERS < LRB_PT_PREFETCH ? S::ITERS : LRB_PT_PREFETCH;   // pairs prefetched across the compute phase
-    constexpr int LANE1 = PT_TO * D;                               // REAL: input distance between the two lanes' streams
+    constexpr int LANE1 = PAY * D;                                 // REAL: input distance between the two lanes' streams
     const float* __restrict__ xr = reinterpret_cast<const float*>(x);
     const float* __restrict__ histr = reinterpret_cast<const float*>(hist);
     extern __shared__ __align__(16) float2 smem[];
@@ -160,7 +172,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         if constexpr (!EDGE) { if (widx >= n_work) break; }
         const long long tile = tile_of(widx);
         const long long B = P.off + tile * (long long)(TS * D);      // first input index of the tile (even)
-        const long long m0 = tile * TS - (DISC ? 1 : 0);             // output index of slot 0
+        const long long m0 = tile * TS - (DISC ? 1 : 0) - PW;        // output index of slot 0
 
         // ---- stage: global -> (x E) -> shared, natural order
         auto stage_pair = [&](float4 v, int it) {
@@ -276,12 +288,44 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         }
 
         const long long mbase = m0 + (long long)tid * PT_R;     // output index of acc[0]
+        if constexpr (POLE) {
+            const float c = P.pole_c;
+            if (tile == 0 && tid < PW / PT_R) {
+                // the stream's first run: the carried state z[-1] takes the place of the warm-up (whose inputs precede
+                // the M-1 samples of history the block keeps)
+#pragma unroll
+                for (int r = 0; r < PT_R; ++r) acc[r].x = 0.f;
+                if (tid == PW / PT_R - 1) acc[PT_R - 1].x = __ldg(reinterpret_cast<const float*>(prev_in));
+            }
+#pragma unroll
+            for (int r = 1; r < PT_R; ++r) acc[r] = __ffma2_rn(acc[r - 1], make_float2(c, c), acc[r]);
+            float2 Bv = acc[PT_R - 1];                        // zero-state end value of this thread's R outputs
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                const float2 o = make_float2(__shfl_up_sync(0xffffffffu, Bv.x, 1 << k), __shfl_up_sync(0xffffffffu, Bv.y, 1 << k));
+                if (lane >= (1 << k)) Bv = __ffma2_rn(o, make_float2(P.pole_cp[k], P.pole_cp[k]), Bv);
+            }
+            if (lane == 31) s_edge[warp] = Bv;
+            float2 prevB = make_float2(__shfl_up_sync(0xffffffffu, Bv.x, 1), __shfl_up_sync(0xffffffffu, Bv.y, 1));
+            if (lane == 0) prevB = make_float2(0.f, 0.f);
+            __syncthreads();                                  // (the tile's last shared-memory read is behind every thread)
+            float2 carryW = make_float2(0.f, 0.f);
+            for (int w = 0; w < warp; ++w) carryW = __ffma2_rn(carryW, make_float2(P.pole_cp[5], P.pole_cp[5]), s_edge[w]);
+            float f_lane = 1.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) if (lane & (1 << k)) f_lane *= P.pole_cp[k];
+            const float2 excl = __ffma2_rn(carryW, make_float2(f_lane, f_lane), prevB);   // z just before acc[0]
+            float cpow = c;
+#pragma unroll
+            for (int r = 0; r < PT_R; ++r) { acc[r] = __ffma2_rn(excl, make_float2(cpow, cpow), acc[r]); cpow *= c; }
+        }
         if constexpr (REAL) {
-            // ---- store: lane 0 -> outputs mbase + r, lane 1 -> outputs mbase + PT_TO + r
+            // ---- store: lane 0 -> outputs mbase + r, lane 1 -> outputs mbase + PAY + r (slots below PW are warm-up)
             float* y = reinterpret_cast<float*>(yv);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const long long mb = mbase + half * PT_TO;
+                const long long mb = mbase + half * PAY;
+                if (POLE && tid < PW / PT_R) continue;
                 float v[PT_R];
 #pragma unroll
                 for (int r = 0; r < PT_R; ++r) v[r] = half ? acc[r].y : acc[r].x;
@@ -293,6 +337,14 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
 #pragma unroll
                     for (int r = 0; r < PT_R; ++r)
                         if (mb + r < n_out) y[mb + r] = v[r];
+                }
+                if constexpr (POLE) {
+                    // the call's last output is the carried state of the next call
+                    if (mb <= n_out - 1 && n_out - 1 < mb + PT_R) {
+#pragma unroll
+                        for (int r = 0; r < PT_R; ++r)
+                            if (mb + r == n_out - 1) *reinterpret_cast<float*>(prev_out) = v[r];
+                    }
                 }
             }
             __syncthreads();                               // shared tile is reused by the next iteration
@@ -360,7 +412,7 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
     }
 }
 
-template <int D, int Q, bool ROT, bool DISC, bool REAL = false>
+template <int D, int Q, bool ROT, bool DISC, bool REAL = false, bool POLE = false>
 int launch_shape(PolyParams P, const float* hr_base, const float2* x, const float2* hist, long long n,
                  void* y, long long first, long long n_out, const float2* prev_in, float2* prev_out, float inv_gain,
                  cudaStream_t s) {
@@ -371,8 +423,8 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
     static int ctas_dev[LRB_MAX_DEVICES] = {0};
     bool& configured = configured_dev[ctx().device & (LRB_MAX_DEVICES - 1)];
     int& ctas_per_sm = ctas_dev[ctx().device & (LRB_MAX_DEVICES - 1)];
-    auto kern_i = polyphase_crcf_kernel<D, Q, ROT, DISC, false, REAL>;
-    auto kern_e = polyphase_crcf_kernel<D, Q, ROT, DISC, true, REAL>;
+    auto kern_i = polyphase_crcf_kernel<D, Q, ROT, DISC, false, REAL, POLE>;
+    auto kern_e = polyphase_crcf_kernel<D, Q, ROT, DISC, true, REAL, POLE>;
     if (!configured) {
         LRB_CHECK(cudaFuncSetAttribute(kern_i, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
         LRB_CHECK(cudaFuncSetAttribute(kern_e, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::SMEM));
@@ -380,9 +432,11 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
         if (ctas_per_sm < 1) ctas_per_sm = 1;
         configured = true;
     }
-    constexpr int TS = REAL ? 2 * PT_TO : TileStride<DISC>::TS;
-    // B(tile) = first + m0*D - (Q*D - 1) - shift, m0 = tile*TS - (DISC ? 1 : 0); shift in {0,1} makes it even
-    long long off = first - (DISC ? D : 0) - (long long)(Q * D - 1);
+    constexpr int PW = POLE ? PT_POLE_WARM : 0;
+    constexpr int PAY = PT_TO - PW;
+    constexpr int TS = REAL ? 2 * PAY : TileStride<DISC>::TS;
+    // B(tile) = first + m0*D - (Q*D - 1) - shift, m0 = tile*TS - (DISC ? 1 : 0) - PW; shift in {0,1} makes it even
+    long long off = first - (DISC ? D : 0) - (long long)PW * D - (long long)(Q * D - 1);
     const int shift = (int)(((off % 2) + 2) % 2);
     off -= shift;
     P.off = off;
@@ -397,7 +451,7 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
     if ((reinterpret_cast<uintptr_t>(x) & (REAL ? 7 : 15)) == 0) {
         const long long step = (long long)TS * D;
         t_lo = off >= 0 ? 0 : (-off + step - 1) / step;
-        const long long lim = n - (long long)S::LOADED - off - (REAL ? (long long)PT_TO * D : 0);
+        const long long lim = n - (long long)S::LOADED - off - (REAL ? (long long)PAY * D : 0);
         t_hi = lim < 0 ? 0 : lim / step + 1;
         if (t_hi > tiles) t_hi = tiles;
         if (t_lo > t_hi) t_lo = t_hi;
@@ -511,8 +565,17 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
     P.M = p->M;
     if (p->real_data) {
         if (rot || disc) { set_error("polyphase: the real-stream kernel has no translator / discriminator"); return -1; }
+        const bool pole = prev_in != nullptr;
+        if (pole) {
+            // inv_gain carries the pole c; prev_in / prev_out its carried state (float32)
+            const double c = (double)inv_gain;
+            P.pole_c = inv_gain;
+            double pw = std::pow(c, (double)PT_R);
+            for (int k = 0; k < 6; ++k) { P.pole_cp[k] = (float)pw; pw = pw * pw; }
+        }
         if (p->D == 5 && p->Q == 27)
-            return launch_shape<5, 27, false, false, true>(P, p->hr, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);
+            return pole ? launch_shape<5, 27, false, false, true, true>(P, p->hr, x, hist, n, y, first, n_out, prev_in, prev_out, 0.f, s)
+                        : launch_shape<5, 27, false, false, true, false>(P, p->hr, x, hist, n, y, first, n_out, nullptr, nullptr, 0.f, s);
         return 0;
     }
     LRB_SHAPE_PLAIN(1, 16) LRB_SHAPE_PLAIN(1, 32)
@@ -520,9 +583,12 @@ static int launch_polyphase_any(const PolyTaps* p, const float2* x, const float2
     return 0;
 }
 
+bool polyphase_pole_ok(float c) { return std::pow(std::fabs((double)c), (double)PT_POLE_WARM) <= 1e-8; }
+
 int launch_polyphase_rrrf(const PolyTaps* p, const float* x, const float* hist, long long n, float* y,
-                          long long first, long long n_out, cudaStream_t s) {
-    return launch_polyphase_any(p, (const float2*)x, (const float2*)hist, n, y, first, n_out, false, false, 0, nullptr, nullptr, 0.f, s);
+                          long long first, long long n_out, cudaStream_t s, float pole_c, const float* z_in, float* z_out) {
+    return launch_polyphase_any(p, (const float2*)x, (const float2*)hist, n, y, first, n_out, false, false, 0,
+                                (const float2*)z_in, (float2*)z_out, pole_c, s);
 }
 
 int launch_polyphase_crcf(const PolyTaps* p, const float2* x, const float2* hist, long long n, float2* y,
@@ -570,6 +636,8 @@ struct TunerBlock : Block {
     }
     size_t max_output(size_t n) const override { return n / D + 1; }
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
+    long long memory_in() const override { return M - 1 + (disc ? D : 0); }
+    void rate(unsigned* up, unsigned* down) const override { *up = 1; *down = (unsigned)D; }
     void reset_host() override { consumed = 0; cur = pcur = 0; }
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override {
         const size_t hb = (size_t)(M > 1 ? M - 1 : 1) * 8;
@@ -585,7 +653,7 @@ struct TunerBlock : Block {
         // concurrently with the filter kernels
         cudaStream_t side = s;
         if (M > 1) {
-            side = side_fork(s);
+            if (n >= SIDE_STREAM_MIN) side = side_fork(s);
             if (launch_hist_update(dx, (long long)n, d_hist[cur], d_hist[cur ^ 1], M - 1, 8, side) != 0) return -1;
         }
         int rc = launch_polyphase_any(pt, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, dy, first, no, true,

@@ -57,7 +57,7 @@ def test_audio_tail_noble_identity(chunk):
     x = (0.4 * np.sin(2 * np.pi * 1000 * t) + 0.3 * np.sin(2 * np.pi * 9000 * t) + 0.2 * rng.uniform(-1, 1, n)).astype(np.float32)
     got, top = run_graph(audio_tail_blocks(), x, rate, chunk)
     desc = top.describe_gpu_graph()
-    assert desc == "fir*iir1_rrrf(133,/5)[fused x3] | pole_rrrf", desc
+    assert desc == "fir*iir1_rrrf(133,/5)+pole[fused x3]", desc
     ref = audio_tail_oracle(rate).process(x)
     close(got, ref)
     # chunked == whole to float32 rounding (the streaming state is exact, only summation grouping at tile edges differs)
