@@ -216,7 +216,7 @@ int    lrb200_graph_seek(lrb200_graph_t* g, uint64_t sample_index);
 /* Time-chunk sharding of one stream over several GPUs / processes (the reference has no counterpart --
  * it parallelises by block, radio/core/composite.lua:568-636).  lrb200_graph_halo: input samples of left context a
  * cold start needs before the outputs equal the streaming ones to float32 resolution (FIR histories, single-pole
- * decay to 1e-12, one discriminator sample), rounded up to whole output periods; < 0 if some stage has unbounded
+ * decay to 1e-12, one discriminator sample), rounded up to 4 whole output periods (keeps buffers 16-byte aligned); < 0 if some stage has unbounded
  * memory.  lrb200_graph_execute_shard runs one chunk: dx -> DEVICE [halo samples of the left neighbour | n samples of
  * this chunk], the chunk starting at global input index `start`; the chunk's kernels start at once, only a head piece
  * of 2*halo samples (run by g_head, a second identical graph, on its own stream) waits for `halo_ready_event`

@@ -1,8 +1,9 @@
 ---
--- The remaining hot-path blocks: each function below is the `if platform.features.cuda then` branch for
+-- The remaining hot-path blocks: each b200.install() below is the `if platform.features.cuda then` branch for
 -- the file named in its comment.  Apply with  require('radio_b200.blocks_patch')(require('radio')).
+-- Every block gets initialize() (HOST-pointer handle for its own process()) and make_device_handle() (the same
+-- create call with DEVICE pointers, used by the scheduler in composite_patch.lua).
 
-local math = require('math')
 local ffi = require('ffi')
 local platform = require('radio.core.platform')
 local types = require('radio.types')
@@ -11,77 +12,65 @@ local b200 = require('radio_b200.platform')
 return function (radio)
     if not platform.features.cuda then return end
     local lib = platform.libs.cuda
+    local function in_type(self) return self:get_input_type() end
+    local function complex_out() return types.ComplexFloat32 end
+    local function real_out() return types.Float32 end
+    local function elem_size(self) return self:get_input_type() == types.ComplexFloat32 and 8 or 4 end
 
     require('radio_b200.firfilter_patch')(radio.FIRFilterBlock)
 
     -- radio/blocks/signal/frequencytranslator.lua:32 (before the volk branch)
-    function radio.FrequencyTranslatorBlock:initialize()
-        self.handle = b200.own(lib.lrb200_rotator_create(self.offset / self:get_rate(), b200.HOST), "rotator")
-        self.out = types.ComplexFloat32.vector()
-    end
+    b200.install(radio.FrequencyTranslatorBlock, "rotator", function (self, flags)
+        return lib.lrb200_rotator_create(self.offset / self:get_rate(), flags)
+    end, complex_out)
     radio.FrequencyTranslatorBlock.process = b200.process
 
     -- radio/blocks/signal/frequencydiscriminator.lua:33-40
-    function radio.FrequencyDiscriminatorBlock:initialize()
-        self.handle = b200.own(lib.lrb200_discrim_create(self.gain, b200.HOST), "discriminator")
-        self.out = types.Float32.vector()
-    end
+    b200.install(radio.FrequencyDiscriminatorBlock, "discriminator", function (self, flags)
+        return lib.lrb200_discrim_create(self.gain, flags)
+    end, real_out)
     radio.FrequencyDiscriminatorBlock.process = b200.process
 
     -- radio/blocks/signal/downsampler.lua:40-56
-    function radio.DownsamplerBlock:initialize()
-        local data_type = self:get_input_type()
-        self.handle = b200.own(lib.lrb200_downsample_create(self.factor, data_type == types.ComplexFloat32 and 8 or 4, b200.HOST), "downsampler")
-        self.out = data_type.vector()
-    end
+    b200.install(radio.DownsamplerBlock, "downsampler", function (self, flags)
+        return lib.lrb200_downsample_create(self.factor, elem_size(self), flags)
+    end, in_type)
     radio.DownsamplerBlock.process = b200.process
 
     -- radio/blocks/signal/iirfilter.lua:63 (before the liquid branch); Singlepole*/FMDeemphasis inherit it
-    function radio.IIRFilterBlock:initialize()
-        local data_type = self:get_input_type()
-        local create = data_type == types.ComplexFloat32 and lib.lrb200_iir_create_crcf or lib.lrb200_iir_create_rrrf
-        self.handle = b200.own(create(self.b_taps.data, self.b_taps.length, self.a_taps.data, self.a_taps.length, b200.HOST), "iir")
-        self.out = data_type.vector()
-    end
+    b200.install(radio.IIRFilterBlock, "iir", function (self, flags)
+        local create = self:get_input_type() == types.ComplexFloat32 and lib.lrb200_iir_create_crcf or lib.lrb200_iir_create_rrrf
+        return create(self.b_taps.data, self.b_taps.length, self.a_taps.data, self.a_taps.length, flags)
+    end, in_type)
     radio.IIRFilterBlock.process_complex = b200.process
     radio.IIRFilterBlock.process_real = b200.process
 
     -- radio/blocks/signal/hilberttransform.lua:39
-    function radio.HilbertTransformBlock:initialize()
-        self.handle = b200.own(lib.lrb200_hilbert_create(self.hilbert_taps.data, self.hilbert_taps.length, b200.HOST), "hilbert")
-        self.out = types.ComplexFloat32.vector()
-    end
+    b200.install(radio.HilbertTransformBlock, "hilbert", function (self, flags)
+        return lib.lrb200_hilbert_create(self.hilbert_taps.data, self.hilbert_taps.length, flags)
+    end, complex_out)
     radio.HilbertTransformBlock.process = b200.process
 
     -- radio/blocks/signal/complexmagnitude.lua:24-36, complextoreal.lua:23-35
-    function radio.ComplexMagnitudeBlock:initialize()
-        self.handle = b200.own(lib.lrb200_cmag_create(b200.HOST), "cmag")
-        self.out = types.Float32.vector()
-    end
+    b200.install(radio.ComplexMagnitudeBlock, "cmag", function (self, flags) return lib.lrb200_cmag_create(flags) end, real_out)
     radio.ComplexMagnitudeBlock.process = b200.process
-    function radio.ComplexToRealBlock:initialize()
-        self.handle = b200.own(lib.lrb200_c2r_create(b200.HOST), "c2r")
-        self.out = types.Float32.vector()
-    end
+    b200.install(radio.ComplexToRealBlock, "c2r", function (self, flags) return lib.lrb200_c2r_create(flags) end, real_out)
     radio.ComplexToRealBlock.process = b200.process
 
     -- radio/blocks/signal/upsampler.lua:36-52 and multiplyconstant.lua:44-70 (resampling family, SURVEY 8f row 4).
     -- InterpolatorBlock / RationalResamplerBlock stay the composites they are; in a GPU sub-graph the three or four
     -- handles are committed to one polyphase kernel (composite_patch.lua -> lrb200_graph_commit).
-    function radio.UpsamplerBlock:initialize()
-        local data_type = self:get_input_type()
-        self.handle = b200.own(lib.lrb200_upsample_create(self.factor, data_type == types.ComplexFloat32 and 8 or 4, b200.HOST), "upsampler")
-        self.out = data_type.vector()
-    end
+    b200.install(radio.UpsamplerBlock, "upsampler", function (self, flags)
+        return lib.lrb200_upsample_create(self.factor, elem_size(self), flags)
+    end, in_type)
     radio.UpsamplerBlock.process = b200.process
-    function radio.MultiplyConstantBlock:initialize()
+    b200.install(radio.MultiplyConstantBlock, "mulconst", function (self, flags)
         local cplx_data = self:get_input_type() == types.ComplexFloat32
         local c = self.constant
         local cplx_const = ffi.istype(types.ComplexFloat32, c)
-        self.handle = b200.own(lib.lrb200_mulconst_create(cplx_const and c.real or c.value, cplx_const and c.imag or 0,
-                                                          cplx_data and 1 or 0, cplx_const and 1 or 0, b200.HOST), "mulconst")
-        self.out = self:get_output_type().vector()
-    end
+        return lib.lrb200_mulconst_create(cplx_const and c.real or c.value, cplx_const and c.imag or 0,
+                                          cplx_data and 1 or 0, cplx_const and 1 or 0, flags)
+    end, function (self) return self:get_output_type() end)
     radio.MultiplyConstantBlock.process = b200.process
     radio.MultiplyConstantBlock.process_complex_by_real = b200.process
 
@@ -96,7 +85,7 @@ return function (radio)
             self.handle = self.handle or b200.own(create(self.format_name, b200.HOST), what)
             local out, n_out = self.out:resize(n), ffi.new("size_t[1]")
             if lib.lrb200_block_execute(self.handle, self.raw_samples.data, n, out.data, n_out) ~= 0 then
-                error(what .. ": " .. ffi.string(lib.lrb200_last_error()))
+                b200.fail(what)
             end
             return out
         end
@@ -110,7 +99,7 @@ return function (radio)
             self.raw_samples:resize(x.length)
             local n_out = ffi.new("size_t[1]")
             if lib.lrb200_block_execute(self.handle, x.data, x.length, self.raw_samples.data, n_out) ~= 0 then
-                error(what .. ": " .. ffi.string(lib.lrb200_last_error()))
+                b200.fail(what)
             end
             if ffi.C.fwrite(self.raw_samples.data, ffi.sizeof(self.raw_samples.data_type), x.length, self.file) ~= x.length then
                 error("fwrite(): " .. ffi.string(ffi.C.strerror(ffi.errno())))
@@ -121,4 +110,7 @@ return function (radio)
     radio.IQFileSink.process = sink_process(lib.lrb200_iqsink_create, "iqsink")
     radio.RealFileSink.process = sink_process(lib.lrb200_realsink_create, "realsink")
     -- format_name: the constructor keeps the format string next to self.format (one added line in each instantiate()).
+
+    -- the scheduler: connected GPU blocks share one device-resident flow graph (composite_patch.lua)
+    require('radio_b200.composite_patch').install(radio)
 end

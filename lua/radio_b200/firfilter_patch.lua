@@ -14,19 +14,22 @@ return function (FIRFilterBlock)
     if not platform.features.cuda then return end
     local lib = platform.libs.cuda
 
-    function FIRFilterBlock:initialize()
+    b200.install(FIRFilterBlock, "fir", function (self, flags)
         local data_type = self:get_input_type()
+        local h
         if data_type == types.ComplexFloat32 and self.taps.data_type == types.Float32 then
-            self.handle = b200.own(lib.lrb200_fir_create_crcf(self.taps.data, self.taps.length, 1, b200.HOST), "fir")
+            h = lib.lrb200_fir_create_crcf(self.taps.data, self.taps.length, 1, flags)
         elseif data_type == types.Float32 and self.taps.data_type == types.Float32 then
-            self.handle = b200.own(lib.lrb200_fir_create_rrrf(self.taps.data, self.taps.length, 1, b200.HOST), "fir")
+            h = lib.lrb200_fir_create_rrrf(self.taps.data, self.taps.length, 1, flags)
         else
-            self.handle = b200.own(lib.lrb200_fir_create_cccf(self.taps.data, self.taps.length, 1, b200.HOST), "fir")
+            h = lib.lrb200_fir_create_cccf(self.taps.data, self.taps.length, 1, flags)
         end
         -- FIRFilterBlock(taps, use_fft): true -> fused overlap-save, false -> direct form, nil -> automatic
-        if self.use_fft ~= nil then lib.lrb200_fir_set_algorithm(self.handle, self.use_fft and 2 or 1) end
-        self.out = data_type.vector()
-    end
+        if h ~= nil and self.use_fft ~= nil then
+            lib.lrb200_fir_set_algorithm(h, self.use_fft and b200.FIR_FFT or b200.FIR_DIRECT)
+        end
+        return h
+    end, function (self) return self:get_input_type() end)
 
     -- length-preserving for every algorithm (the GPU block never delays/chunks like process_fft)
     FIRFilterBlock.process_complex_input_complex_taps = b200.process

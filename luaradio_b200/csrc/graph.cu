@@ -473,7 +473,9 @@ struct Graph {
         }
         unsigned long long up, down;
         total_rate(&up, &down);
-        const long long q = (long long)down;                 // input samples per whole output period
+        // whole output periods, and a multiple of 4 samples so that a chunk placed `halo` samples into a 16-byte aligned
+        // buffer stays 16-byte aligned (float32 and complex streams alike): the vectorised interior kernels need that
+        const long long q = 4 * (long long)down;
         long long h = (long long)need;
         h = ((h + q - 1) / q) * q;
         return h;

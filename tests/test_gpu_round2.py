@@ -124,3 +124,83 @@ def test_real_polyphase_decimator_c_abi(M, D):
     lib.lrb200_fir_destroy(h)
     ref = O.Chain(O.FIRFilter(taps, False), O.Downsampler(D)).process(x)
     close(np.concatenate(outs), ref)
+
+
+def _chain_graph(lib):
+    import bench
+    return bench.build_chain_graph(lib, _lib)
+
+
+def test_superchunk_mode_equals_synchronous_calls():
+    """lrb200_graph_set_superchunk: the reference's 8192-sample vectors (zero.lua:30) packed into pinned super-chunks and
+    processed asynchronously give the same stream as one synchronous call per vector, after lrb200_graph_flush."""
+    lib = _lib.require_device()
+    n, vec = 1000000, 8192
+    x = O.synth_fm_iq(0, n)
+    g = _chain_graph(lib)
+
+    def run(sc, flush_every=None):
+        _lib.check(lib.lrb200_graph_reset(g))
+        _lib.check(lib.lrb200_graph_set_superchunk(g, sc))
+        cap = lib.lrb200_graph_max_output(g, vec) + 16
+        y = np.zeros(cap, np.float32)
+        no = ctypes.c_size_t()
+        outs, counts = [], []
+        for o in range(0, n, vec):
+            seg = np.ascontiguousarray(x[o:o + vec])
+            _lib.check(lib.lrb200_graph_execute(g, seg.ctypes.data, len(seg), y.ctypes.data, ctypes.byref(no)))
+            assert no.value <= cap
+            counts.append(no.value)
+            outs.append(y[:no.value].copy())
+        _lib.check(lib.lrb200_graph_flush(g, y.ctypes.data, ctypes.byref(no)))
+        outs.append(y[:no.value].copy())
+        _lib.check(lib.lrb200_graph_set_superchunk(g, 0))
+        return np.concatenate(outs), counts
+
+    sync, _ = run(0)
+    ref = O.wbfm_mono_chain().process(x)
+    close(sync, ref)
+    for sc in (1 << 16, 100000, 1 << 20):
+        acc, counts = run(sc)
+        assert acc.shape == sync.shape
+        close(acc, sync, absolute=2e-6)
+        assert counts.count(0) > len(counts) // 2         # most calls only append to the pinned slot
+    lib.lrb200_graph_destroy(g)
+
+
+def test_graph_halo_and_execute_shard_on_one_device():
+    """lrb200_graph_halo / lrb200_graph_execute_shard: the chunks of a 4-way time-sharded stream, each run cold with only a
+    head piece depending on the left neighbour's samples, concatenate to the single-stream result."""
+    lib = _lib.require_device()
+    total, world = 2000000, 4
+    x = O.synth_fm_iq(0, total)
+    g, gh = _chain_graph(lib), _chain_graph(lib)
+    halo = lib.lrb200_graph_halo(g)
+    assert halo % 25 == 0 and 2500 <= halo <= 4000, halo
+    whole = np.zeros(total // 25 + 8, np.float32)
+    no = ctypes.c_size_t()
+    _lib.check(lib.lrb200_graph_execute(g, x.ctypes.data, total, whole.ctypes.data, ctypes.byref(no)))
+    whole = whole[:no.value]
+    per = total // world
+    assert per % 25 == 0
+    d_in = lib.lrb200_malloc((per + halo) * 8)
+    d_out = lib.lrb200_malloc((per // 25 + 8) * 4)
+    parts = []
+    for r in range(world):
+        start = r * per
+        lead = halo if r > 0 else 0
+        seg = np.ascontiguousarray(x[start - lead:start + per])
+        _lib.check(lib.lrb200_memcpy_h2d(ctypes.c_void_p(d_in + (halo - lead) * 8), seg.ctypes.data, seg.nbytes))
+        _lib.check(lib.lrb200_graph_execute_shard(g, gh, ctypes.c_void_p(d_in), halo, per, start, ctypes.c_void_p(d_out),
+                                                  ctypes.byref(no), None))
+        out = np.zeros(no.value, np.float32)
+        _lib.check(lib.lrb200_memcpy_d2h(out.ctypes.data, ctypes.c_void_p(d_out), out.nbytes))
+        _lib.check(lib.lrb200_sync())
+        parts.append(out)
+    got = np.concatenate(parts)
+    assert got.shape == whole.shape
+    close(got, whole, absolute=2e-6)
+    lib.lrb200_free(d_in)
+    lib.lrb200_free(d_out)
+    lib.lrb200_graph_destroy(g)
+    lib.lrb200_graph_destroy(gh)

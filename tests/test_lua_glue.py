@@ -1,0 +1,106 @@
+"""Static checks of the LuaJIT glue (lua/radio_b200/*.lua).  LuaJIT is not installed in the build image, so the glue is
+never executed here; these tests make it reviewable instead: the FFI declarations are GENERATED from include/lrb200.h
+and must be current, every lrb200_* symbol the Lua code calls must be declared (LuaJIT raises "missing declaration"
+otherwise), every helper / method it calls must be defined by the glue or be part of the reference's block API, and the
+block structure of every file must balance."""
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LUA = os.path.join(ROOT, "lua", "radio_b200")
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_lua_cdef  # noqa: E402
+
+from luaradio_b200 import _lib  # noqa: E402
+
+# methods of the reference's own classes that the glue calls (radio/core/block.lua:238-390,516-532; radio/core/vector.lua:108-136;
+# radio/core/pipe.lua:495-615; radio/core/platform.lua:277-285)
+REFERENCE_METHODS = {
+    "add_type_signature", "get_input_type", "get_output_type", "get_rate", "differentiate", "resize", "write", "vector",
+}
+
+
+def lua_files():
+    return sorted(f for f in os.listdir(LUA) if f.endswith(".lua"))
+
+
+def strip_lua(text):
+    """Lua source without comments and string literals (long brackets included)."""
+    text = re.sub(r"--\[\[.*?\]\]", " ", text, flags=re.S)
+    text = re.sub(r"\[\[.*?\]\]", '""', text, flags=re.S)
+    text = re.sub(r"--[^\n]*", " ", text)
+    text = re.sub(r'"(?:\\.|[^"\\])*"', '""', text)
+    text = re.sub(r"'(?:\\.|[^'\\])*'", "''", text)
+    return text
+
+
+def test_cdef_is_generated_from_the_header_and_current():
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_lua_cdef.py"), "--check"]).returncode == 0, \
+        "lua/radio_b200/cdef.lua is stale: run python tools/gen_lua_cdef.py"
+    header = gen_lua_cdef.header_statements(open(gen_lua_cdef.HEADER).read())
+    body = open(os.path.join(LUA, "cdef.lua")).read()
+    body = body[body.index("[[") + 2: body.index("]]")]
+    declared = [gen_lua_cdef.normalise(s) for s in body.split(";") if s.strip()]
+    assert declared == header                                   # prototypes textually equal after normalisation
+    fns = gen_lua_cdef.function_names(header)
+    assert sorted(fns) == _lib.EXPORTED_SYMBOLS                  # == what ctypes binds == what the .so exports (test_cpu_host)
+    # the two sample types are LuaRadio's own (radio/types): the cdef must not redefine them
+    assert "typedef struct {" not in body
+
+
+def test_every_library_call_in_the_glue_is_declared():
+    declared = set(gen_lua_cdef.function_names(gen_lua_cdef.header_statements(open(gen_lua_cdef.HEADER).read())))
+    used = {}
+    for f in lua_files():
+        if f == "cdef.lua":
+            continue
+        text = strip_lua(open(os.path.join(LUA, f)).read())
+        for m in re.finditer(r"\b(lrb200_\w+)\b", text):
+            used.setdefault(m.group(1), set()).add(f)
+    assert used, "no library calls found: the scan is broken"
+    missing = {k: sorted(v) for k, v in used.items() if k not in declared}
+    assert not missing, "called from Lua but not in the cdef: %s" % missing
+    # the blocks of the hot path are all bound
+    for need in ("lrb200_fir_create_crcf", "lrb200_rotator_create", "lrb200_discrim_create", "lrb200_downsample_create",
+                 "lrb200_iir_create_rrrf", "lrb200_graph_execute", "lrb200_graph_commit", "lrb200_graph_flush",
+                 "lrb200_mulconst_create", "lrb200_upsample_create"):
+        assert need in used, need
+
+
+def test_helpers_and_methods_the_glue_calls_exist():
+    texts = {f: strip_lua(open(os.path.join(LUA, f)).read()) for f in lua_files() if f != "cdef.lua"}
+    # helpers of radio_b200.platform (module table M) used as b200.<name>
+    plat = texts["platform.lua"]
+    defined_m = set(re.findall(r"function M\.(\w+)", plat)) | set(re.findall(r"\bM\.(\w+)\s*=", plat)) | \
+        set(re.findall(r"\b(\w+)\s*=\s*decl\.constants", plat))
+    for f, t in texts.items():
+        for name in re.findall(r"\bb200\.(\w+)", t):
+            assert name in defined_m, "%s uses b200.%s which radio_b200/platform.lua does not define" % (f, name)
+    # methods called with ':' -- defined somewhere in the glue, or part of the reference API
+    defined_methods = set()
+    for t in texts.values():
+        defined_methods |= set(re.findall(r"function \w+(?:\.\w+)*:(\w+)\s*\(", t))
+    for f, t in texts.items():
+        for obj, name in re.findall(r"\b(\w+(?:\[[^\]]*\])?(?:\.\w+)*):(\w+)\s*\(", t):
+            assert name in defined_methods or name in REFERENCE_METHODS, "%s calls %s:%s() which nothing defines" % (f, obj, name)
+    # the scheduler hook is really installed, and the block hook really defines make_device_handle
+    assert "make_device_handle" in defined_methods
+    comp = texts["composite_patch.lua"]
+    assert re.search(r"function CompositeBlock:start\(", comp) and re.search(r"function CompositeBlock:_crawl_connections\(", comp)
+    assert "composite_patch').install(radio)" in open(os.path.join(LUA, "blocks_patch.lua")).read()
+    # module-level functions used inside composite_patch are defined there
+    for name in re.findall(r"\bM\.(\w+)\(", comp):
+        assert re.search(r"function M\.%s\(" % name, comp), name
+
+
+def test_lua_block_structure_balances():
+    for f in lua_files():
+        words = re.findall(r"[A-Za-z_]\w*", strip_lua(open(os.path.join(LUA, f)).read()))
+        opens = sum(words.count(w) for w in ("function", "if", "do"))
+        assert opens == words.count("end"), "%s: %d block openers vs %d `end`" % (f, opens, words.count("end"))
+        assert words.count("repeat") == words.count("until")
+        text = strip_lua(open(os.path.join(LUA, f)).read())
+        for a, b in ("()", "{}", "[]"):
+            assert text.count(a) == text.count(b), "%s: unbalanced %s%s" % (f, a, b)
