@@ -77,6 +77,12 @@ int   lrb200_memset(void* dptr, int value, size_t bytes);
 typedef struct lrb200_block_s lrb200_block_t;
 
 int    lrb200_block_execute(lrb200_block_t* q, const void* x, size_t n, void* y, size_t* n_out);
+/* blocks with several ports (block.lua:516-532 hands process() one vector per input, all of the same length n):
+ * x[i] / y[o] are the port buffers, in the handle's pointer mode */
+int    lrb200_block_execute_multi(lrb200_block_t* q, const void* const* x, unsigned num_inputs, size_t n, void* const* y,
+                                  unsigned num_outputs, size_t* n_out);
+unsigned lrb200_block_num_inputs(const lrb200_block_t* q);
+unsigned lrb200_block_num_outputs(const lrb200_block_t* q);
 size_t lrb200_block_max_output(const lrb200_block_t* q, size_t n); /* upper bound on *n_out for n inputs */
 size_t lrb200_block_in_size(const lrb200_block_t* q);              /* bytes per input sample  */
 size_t lrb200_block_out_size(const lrb200_block_t* q);             /* bytes per output sample */
@@ -166,6 +172,28 @@ lrb200_block_t* lrb200_c2r_create(unsigned flags);
  * -- commit to ONE polyphase kernel that touches only the non-zero products of kept outputs. */
 lrb200_block_t* lrb200_mulconst_create(float re, float im, unsigned complex_data, unsigned complex_constant, unsigned flags);
 lrb200_block_t* lrb200_upsample_create(unsigned factor, unsigned elem_size, unsigned flags);
+
+/* ---- Two-input element-wise blocks, DelayBlock, PSD -------------------------------------
+ * lrb200_binary_create replaces MultiplyBlock / MultiplyConjugateBlock / AddBlock / SubtractBlock:process
+ * (radio/blocks/signal/multiply.lua, multiplyconjugate.lua:26-51, add.lua, subtract.lua; VOLK or Lua loops):
+ * op = "multiply" | "multiplyconjugate" (y = a * conj(b), complex only) | "add" | "subtract"; both inputs and the output
+ * are ComplexFloat32 (complex_data != 0) or Float32.  Execute through lrb200_block_execute_multi with two inputs.
+ * lrb200_delay_create replaces DelayBlock:process (radio/blocks/signal/delay.lua:26-60): y[n] = x[n - num_samples],
+ * zeros first, the last num_samples inputs carried.
+ * lrb200_psd_create replaces spectrum_utils.PSD:compute (radio/utilities/spectrum_utils.lua:524-642), the engine of the
+ * spectrum sinks: every whole frame of num_samples inputs (power of two <= 4096) is multiplied by `window`
+ * (window_utils.window(N, type, true)), transformed, and |X_k|^2 / scale (scale = sample_rate * window energy) is written,
+ * as 10*log10 of it when logarithmic != 0; n must be a multiple of num_samples.
+ * lrb200_pll_create replaces PLLBlock:process (radio/blocks/signal/pll.lua:113-170): loop constants from
+ * (loop_bandwidth, frequency_min, frequency_max) in Hz at `rate`, output 0 = exp(j phi_multiplied) (ComplexFloat32),
+ * output 1 = phase error (Float32); execute through lrb200_block_execute_multi with one input and two outputs.  The
+ * recurrence is nonlinear and is run in stream order by one thread (exact, a few MS/s). */
+lrb200_block_t* lrb200_binary_create(const char* op, unsigned complex_data, unsigned flags);
+lrb200_block_t* lrb200_pll_create(double loop_bandwidth, double frequency_min, double frequency_max, double multiplier,
+                                  double rate, unsigned flags);
+lrb200_block_t* lrb200_delay_create(unsigned num_samples, unsigned elem_size, unsigned flags);
+lrb200_block_t* lrb200_psd_create(unsigned num_samples, const float32_t* window, double scale, unsigned logarithmic,
+                                  unsigned complex_data, unsigned flags);
 
 /* ---- IQFileSource sample formats (the source boundary) ------------------------------
  * Replaces the byte-swap + (value - offset) / scale loops of radio/blocks/sources/iqfile.lua:96-108 with the format

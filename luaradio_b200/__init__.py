@@ -16,14 +16,16 @@ from . import _lib, block, types
 from .block import Block, Input, Output, factory
 from .composite import (AMEnvelopeDemodulator, ArraySink, ArraySource, CompositeBlock, DecimatorBlock, InterpolatorBlock,
                         IQFileSink, IQFileSource, NBFMDemodulator, RationalResamplerBlock, RawFileSink, RawFileSource,
-                        RealFileSink, RealFileSource, SSBDemodulator, TunerBlock, WAVFileSink, WBFMMonoDemodulator)
+                        RealFileSink, RealFileSource, SSBDemodulator, TunerBlock, WAVFileSink, WBFMMonoDemodulator,
+                        WBFMStereoDemodulator, AMSynchronousDemodulator, GPUChainBlock)
 from .signal_blocks import (MultiplyConstantBlock, UpsamplerBlock, BandpassFilterBlock, BandstopFilterBlock, ComplexBandpassFilterBlock,
                             ComplexBandstopFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,
                             DownsamplerBlock, FIRFilterBlock, FMDeemphasisFilterBlock,
                             FrequencyDiscriminatorBlock, FrequencyTranslatorBlock, GPUBlock,
                             HighpassFilterBlock, HilbertTransformBlock, IIRFilterBlock, LowpassFilterBlock,
-                            SinglepoleHighpassFilterBlock, SinglepoleLowpassFilterBlock)
+                            SinglepoleHighpassFilterBlock, SinglepoleLowpassFilterBlock,
+                            MultiplyBlock, MultiplyConjugateBlock, AddBlock, SubtractBlock, DelayBlock, PLLBlock, GPUMultiBlock)
 from .types import ComplexFloat32, Float32, Vector
-from .utilities import filter_utils, window_utils
+from .utilities import filter_utils, spectrum_utils, window_utils
 
 __version__ = "0.1.0"

@@ -36,6 +36,13 @@ _PROTOS = {
     "lrb200_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_size_t]),
     "lrb200_memset": (c_int, [c_void_p, c_int, c_size_t]),
     "lrb200_block_execute": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
+    "lrb200_block_execute_multi": (c_int, [c_void_p, POINTER(c_void_p), c_uint, c_size_t, POINTER(c_void_p), c_uint, POINTER(c_size_t)]),
+    "lrb200_block_num_inputs": (c_uint, [c_void_p]),
+    "lrb200_block_num_outputs": (c_uint, [c_void_p]),
+    "lrb200_binary_create": (c_void_p, [c_char_p, c_uint, c_uint]),
+    "lrb200_delay_create": (c_void_p, [c_uint, c_uint, c_uint]),
+    "lrb200_pll_create": (c_void_p, [c_double, c_double, c_double, c_double, c_double, c_uint]),
+    "lrb200_psd_create": (c_void_p, [c_uint, c_void_p, c_double, c_uint, c_uint, c_uint]),
     "lrb200_block_max_output": (c_size_t, [c_void_p, c_size_t]),
     "lrb200_block_in_size": (c_size_t, [c_void_p]),
     "lrb200_block_out_size": (c_size_t, [c_void_p]),

@@ -3,13 +3,17 @@
 Graph building mirrors radio/core/composite.lua:111-216 (connect / aliasing), :302-424 (validate,
 differentiate in evaluation order, crawl hierarchical blocks down to concrete ports, connect pipes,
 validate rates, initialize).  Running differs by design (north_star): instead of fork-per-block over
-socketpairs (composite.lua:568-636) the graph runs in ONE process on ONE CUDA stream.  A linear run of
-GPU blocks between a source and a sink is handed to the library's flow graph (lrb200_graph_*), where
-the blocks share device-resident buffers and adjacent blocks are fused; host<->device copies happen
-only at the source and sink.  Non-linear graphs run block-by-block in evaluation order (the
-reference's run(false) round-robin, composite.lua:647-707), each block's process() still on the GPU.
+socketpairs (composite.lua:568-636) the graph runs in ONE process on ONE CUDA stream.  Every MAXIMAL LINEAR
+RUN of GPU blocks in the flattened graph -- wherever it sits in an arbitrary DAG -- is replaced by one
+GPUChainBlock backed by the library's flow graph (lrb200_graph_*), where the blocks share device-resident
+buffers and adjacent blocks are fused; host<->device copies happen only at the two ends of each run.  The
+reduced graph (sources, chains, CPU blocks, multi-input blocks, sinks) runs in evaluation order like the
+reference's run(false) round-robin (composite.lua:647-707).  start()/wait()/stop()/status() have the
+reference's meaning (composite.lua:534-545, 858-913) on a scheduler thread.
 """
 import ctypes
+import sys
+import threading
 
 import numpy as np
 
@@ -17,7 +21,8 @@ from . import _lib
 from .block import Block, Input, Output, Pipe, Port
 from .signal_blocks import (MultiplyConstantBlock, UpsamplerBlock, ComplexBandpassFilterBlock, ComplexMagnitudeBlock, ComplexToRealBlock,
                             SinglepoleHighpassFilterBlock, DownsamplerBlock, FMDeemphasisFilterBlock, FrequencyDiscriminatorBlock,
-                            FrequencyTranslatorBlock, GPUBlock, LowpassFilterBlock)
+                            FrequencyTranslatorBlock, GPUBlock, LowpassFilterBlock, HilbertTransformBlock, DelayBlock, PLLBlock,
+                            MultiplyConjugateBlock, AddBlock, SubtractBlock)
 from .types import ComplexFloat32, Float32, Vector
 
 
@@ -76,26 +81,40 @@ class IQFileSource(Block):
         return self.rate
 
     def initialize(self):
+        # like the reference (fread() of chunk_size samples per process(), iqfile.lua:82-95) the file is read
+        # incrementally, so a pipe (rtl_sdr | ...) streams and a capture larger than RAM works
+        self._buf, self._fh, self._own_fh = None, None, False
         if isinstance(self.file, (bytes, bytearray, memoryview, np.ndarray)):
             self._buf = np.frombuffer(bytes(self.file) if not isinstance(self.file, np.ndarray) else self.file.tobytes(), np.uint8)
         elif isinstance(self.file, str):
-            self._buf = np.fromfile(self.file, np.uint8)
+            self._fh, self._own_fh = open(self.file, "rb"), True
         else:
-            self._buf = np.frombuffer(self.file.read(), np.uint8)
+            self._fh = self.file
         self._pos = 0
+        self._tail = b""
         self.out = self.out_type.vector()
 
-    def read_raw(self):
-        """Next chunk of raw file bytes (whole samples), or None at EOF."""
-        nbytes = self.chunk_size * self.sample_bytes
-        if self._pos >= len(self._buf) - self.sample_bytes + 1:
-            if not self.repeat_on_eof or len(self._buf) < self.sample_bytes:
-                return None
-            self._pos = 0
-        raw = self._buf[self._pos:self._pos + nbytes]
-        raw = raw[:len(raw) // self.sample_bytes * self.sample_bytes]
-        self._pos += len(raw)
-        return np.ascontiguousarray(raw)
+    def read_raw(self, samples=None):
+        """Next chunk of raw file bytes (whole samples; `samples` overrides chunk_size), or None at EOF."""
+        nbytes = (samples or self.chunk_size) * self.sample_bytes
+        if self._buf is not None:
+            if self._pos >= len(self._buf) - self.sample_bytes + 1:
+                if not self.repeat_on_eof or len(self._buf) < self.sample_bytes:
+                    return None
+                self._pos = 0
+            raw = self._buf[self._pos:self._pos + nbytes]
+            raw = raw[:len(raw) // self.sample_bytes * self.sample_bytes]
+            self._pos += len(raw)
+            return np.ascontiguousarray(raw)
+        data = self._tail + (self._fh.read(nbytes - len(self._tail)) or b"")
+        if len(data) < self.sample_bytes and self.repeat_on_eof and self._fh.seekable():
+            self._fh.seek(0)                                   # iqfile.lua:90-93
+            data = self._fh.read(nbytes) or b""
+        whole = len(data) // self.sample_bytes * self.sample_bytes
+        self._tail = data[whole:]
+        if whole == 0:
+            return None
+        return np.frombuffer(data[:whole], np.uint8)
 
     def make_device_handle(self):
         lib = _lib.require_device()
@@ -118,6 +137,9 @@ class IQFileSource(Block):
         if self._handle:
             _lib.load().lrb200_block_destroy(self._handle)
             self._handle = None
+        if getattr(self, "_own_fh", False) and self._fh is not None:
+            self._fh.close()
+            self._fh = None
 
 
 class RealFileSource(IQFileSource):
@@ -449,6 +471,9 @@ class CompositeBlock(Block):
         self._validate_inputs()
         self._differentiate()
         self._all_connections = self._crawl_connections()
+        for inp, outp in self._all_connections.items():      # a second run() starts from clean ports
+            outp.pipes = []
+            inp.pipe = None
         for inp, outp in self._all_connections.items():
             pipe = Pipe(outp, inp)
             outp.pipes.append(pipe)
@@ -466,114 +491,276 @@ class CompositeBlock(Block):
             b.initialize()
 
     # ---------------------------------------------------------------------------------------------
-    def _linear_gpu_chain(self):
-        """[source, gpu blocks..., sink] if the flattened graph is one linear chain, else None."""
-        order = self._concrete_order
-        if len(order) < 3:
-            return None
-        for i, b in enumerate(order):
-            n_in, n_out = len(b.inputs), len(b.outputs)
-            if i == 0 and not (n_in == 0 and n_out == 1 and len(b.outputs[0].pipes) == 1):
-                return None
-            if 0 < i < len(order) - 1 and not (isinstance(b, GPUBlock) and n_in == 1 and n_out == 1 and len(b.outputs[0].pipes) == 1
-                                               and b.inputs[0].pipe.output.owner is order[i - 1]):
-                return None
-            if i == len(order) - 1 and not (n_in == 1 and n_out == 0 and b.inputs[0].pipe.output.owner is order[i - 1]):
-                return None
-        return order
+    # GPU scheduler: maximal linear GPU runs -> GPUChainBlock, then round-robin over the reduced graph
+    # ---------------------------------------------------------------------------------------------
+    def _collapse_gpu_runs(self, fuse, superchunk):
+        """Rewrite (self._all_connections, self._concrete_order): every maximal linear run of GPU blocks becomes one
+        GPUChainBlock (a run of one block keeps the block's own handle unless it borders a raw file source / sink); a raw
+        file source feeding only the run, and a raw file sink fed only by it, are absorbed as its first / last stage."""
+        conns = dict(self._all_connections)
+        consumers = {}
+        for inp, outp in conns.items():
+            consumers.setdefault(outp, []).append(inp)
+
+        def is_gpu(b):
+            return isinstance(b, GPUBlock) and len(b.inputs) == 1 and len(b.outputs) == 1
+
+        def next_in_run(b):
+            c = consumers.get(b.outputs[0], [])
+            return c[0].owner if len(c) == 1 and is_gpu(c[0].owner) else None
+
+        def prev_in_run(b):
+            up = conns[b.inputs[0]].owner
+            return up if is_gpu(up) and next_in_run(up) is b else None
+
+        chains = []
+        for b in list(self._concrete_order):
+            if not is_gpu(b) or prev_in_run(b) is not None:
+                continue
+            run, nb = [b], next_in_run(b)
+            while nb is not None:
+                run.append(nb)
+                nb = next_in_run(nb)
+            up_port = conns[run[0].inputs[0]]
+            src = up_port.owner if getattr(up_port.owner, "raw_source", False) and len(consumers.get(up_port, [])) == 1 else None
+            down = consumers.get(run[-1].outputs[0], [])
+            snk = down[0].owner if len(down) == 1 and getattr(down[0].owner, "raw_sink", False) and len(down[0].owner.inputs) == 1 else None
+            if len(run) < 2 and src is None and snk is None:
+                continue
+            chain = GPUChainBlock(run, src, snk, fuse, superchunk)
+            chains.append(chain)
+            for rb in run:
+                del conns[rb.inputs[0]]
+            if src is None:
+                conns[chain.inputs[0]] = up_port
+                chain.inputs[0].pipe = run[0].inputs[0].pipe          # rate propagation
+            if snk is None:
+                for cin in down:
+                    conns[cin] = chain.outputs[0]
+            else:
+                del conns[snk.inputs[0]]
+        absorbed = set()
+        for c in chains:
+            absorbed.update(c.blocks)
+            absorbed.update(x for x in (c.raw_source, c.raw_sink) if x is not None)
+        blocks = [b for b in self._concrete_order if b not in absorbed] + chains
+        self._chains = chains
+        self._run_connections = conns
+        self._run_order = _evaluation_order(conns, blocks) if conns else blocks
+        for c in chains:
+            c.initialize()
 
     def describe_gpu_graph(self):
-        return self._gpu_desc if getattr(self, "_gpu_desc", None) else ""
+        """The committed device flow graph(s) of the last run: stages separated by ' | ', several runs by ' ; '."""
+        return " ; ".join(c.desc for c in getattr(self, "_chains", []) if c.desc)
 
-    def run(self, multiprocess=False, fuse=True):
-        """Run to source EOF.  `multiprocess` is accepted for API compatibility; the GPU scheduler is
-        always single-process (a CUDA context does not survive fork())."""
-        self._prepare_to_run()
-        chain = self._linear_gpu_chain()
-        if chain is not None:
-            self._run_gpu_chain(chain, fuse)
-        else:
-            self._run_round_robin()
-        for b in self._concrete_order:
-            b.cleanup()
-        return self
+    def _schedule(self):
+        """One process, evaluation order, FIFOs per input port (composite.lua:647-707); at end of stream the chains are
+        flushed (super-chunk mode) and the graph drains."""
+        order, conns = self._run_order, self._run_connections
+        fifo = {inp: [] for inp in conns}
+        consumers = {}
+        for inp, outp in conns.items():
+            consumers.setdefault(outp, []).append(inp)
 
-    def _run_gpu_chain(self, chain, fuse):
-        lib = _lib.require_device()
-        source, sink, blocks = chain[0], chain[-1], chain[1:-1]
-        g = _lib.check_handle(lib.lrb200_graph_create(), "lrb200 graph")
-        raw_source = bool(getattr(source, "raw_source", False))
-        raw_sink = bool(getattr(sink, "raw_sink", False))
-        try:
-            if raw_source:      # the file's sample format is converted on the device, as the first graph stage
-                _lib.check(lib.lrb200_graph_append(g, source.make_device_handle()), "graph_append(iqconv)")
-            for b in blocks:
-                h = b.make_device_handle()
-                _lib.check(lib.lrb200_graph_append(g, h), "graph_append(%s)" % b.name)
-            if raw_sink:        # ... and the sink's file format is produced on the device, as the last stage
-                _lib.check(lib.lrb200_graph_append(g, sink.make_device_handle()), "graph_append(file sink)")
-            _lib.check(lib.lrb200_graph_commit(g, 1 if fuse else 0), "graph_commit")
-            self._gpu_desc = lib.lrb200_graph_describe(g).decode()
-            out_type = blocks[-1].get_output_type()
-            out = out_type.vector()
-            raw_out = np.zeros(0, np.uint8)
-            while True:
-                if raw_source:
-                    raw = source.read_raw()
-                    if raw is None:
-                        break
-                    n_in, in_ptr = len(raw) // source.sample_bytes, raw.ctypes.data
-                else:
-                    x = source.process()
-                    if x is None:
-                        break
-                    n_in, in_ptr = x.length, x.ctypes_ptr()
-                n_out = ctypes.c_size_t(0)
-                if raw_sink:
-                    need = lib.lrb200_graph_max_output(g, n_in) * sink.raw_sample_bytes
-                    if len(raw_out) < need:
-                        raw_out = np.zeros(need, np.uint8)
-                    _lib.check(lib.lrb200_graph_execute(g, in_ptr, n_in, raw_out.ctypes.data, ctypes.byref(n_out)), "graph_execute")
-                    sink.write_raw(raw_out[:n_out.value * sink.raw_sample_bytes], n_out.value)
+        def push(b, outs):
+            for port, vec in zip(b.outputs, outs):
+                if vec is None or vec.length == 0:
                     continue
-                out.resize(lib.lrb200_graph_max_output(g, n_in))
-                _lib.check(lib.lrb200_graph_execute(g, in_ptr, n_in, out.ctypes_ptr(), ctypes.byref(n_out)), "graph_execute")
-                out.resize(n_out.value)
-                sink.process(out)
-        finally:
-            lib.lrb200_graph_destroy(g)
+                data = np.array(vec.data, copy=True)
+                for cin in consumers.get(port, []):
+                    fifo[cin].append(data)
 
-    def _run_round_robin(self):
-        order = self._concrete_order
-        fifo = {}                      # input port -> list of numpy chunks
-        for inp in self._all_connections:
-            fifo[inp] = []
-        live = True
-        while live:
+        exhausted, flushed = set(), False
+        while not self._stop_requested:
             live = False
             for b in order:
                 if not b.inputs:
+                    if b in exhausted:
+                        continue
                     v = b.process()
                     if v is None:
+                        exhausted.add(b)
                         continue
-                    outs = v if isinstance(v, tuple) else (v,)
+                    push(b, v if isinstance(v, tuple) else (v,))
                     live = True
-                else:
-                    if any(len(fifo[p]) == 0 for p in b.inputs):
-                        continue
-                    arrays = [np.concatenate(fifo[p]) if len(fifo[p]) > 1 else fifo[p][0] for p in b.inputs]
-                    n = min(len(a) for a in arrays)
-                    if n == 0:
-                        continue
-                    for p, a in zip(b.inputs, arrays):
-                        fifo[p] = [a[n:]] if len(a) > n else []
-                    r = b.process(*[Vector.cast(a[:n]) for a in arrays])
-                    outs = () if r is None else (r if isinstance(r, tuple) else (r,))
-                    live = True
-                for port, vec in zip(b.outputs, outs):
-                    data = np.array(vec.data, copy=True)
-                    for pipe in port.pipes:
-                        fifo[pipe.input].append(data)
+                    continue
+                if any(len(fifo[p]) == 0 for p in b.inputs):
+                    continue
+                arrays = [np.concatenate(fifo[p]) if len(fifo[p]) > 1 else fifo[p][0] for p in b.inputs]
+                n = min(len(a) for a in arrays)
+                if n == 0:
+                    continue
+                for p, a in zip(b.inputs, arrays):
+                    fifo[p] = [a[n:]] if len(a) > n else []
+                r = b.process(*[Vector.cast(a[:n]) for a in arrays])
+                push(b, () if r is None else (r if isinstance(r, tuple) else (r,)))
+                live = True
+            if live:
+                continue
+            if flushed:
+                break
+            # every source is at EOF and nothing moved: push the pending super-chunks out and drain once more
+            flushed = True
+            for b in order:
+                if isinstance(b, GPUChainBlock):
+                    r = b.flush()
+                    if r is not None:
+                        push(b, (r,))
+
+    def _run_body(self, fuse, superchunk):
+        try:
+            self._collapse_gpu_runs(fuse, superchunk)
+            self._schedule()
+        finally:
+            # composite.lua:693-696: clean up every block, whatever happened (native handles, file sinks, WAV header)
+            pending = sys.exc_info()[0] is not None
+            first = None
+            for b in getattr(self, "_run_order", []) + [x for x in self._concrete_order if x not in getattr(self, "_run_order", [])]:
+                try:
+                    b.cleanup()
+                except Exception as e:          # keep cleaning up; report the first failure unless an error is already in flight
+                    first = first or e
+            if first is not None and not pending:
+                raise first
+
+    # -- composite.lua:534-545 start, :858 status, :886 stop, :913 wait, :937 run
+    def start(self, multiprocess=False, fuse=True, superchunk=0):
+        """Prepare the flow graph and start running it on a scheduler thread.  `multiprocess` is accepted for API
+        compatibility; the GPU scheduler is always single-process (a CUDA context does not survive fork())."""
+        if getattr(self, "_running", False):
+            raise RuntimeError("CompositeBlock already running!")
+        self._prepare_to_run()
+        self._stop_requested, self._error = False, None
+        lib = _lib.load()
+        device = lib.lrb200_current_device()
+
+        def body():
+            try:
+                if device >= 0:
+                    _lib.check(lib.lrb200_init(device), "lrb200_init")      # the CUDA device is a per-thread setting
+                self._run_body(fuse, superchunk)
+            except BaseException as e:      # surfaced by wait()
+                self._error = e
+            finally:
+                self._running = False
+
+        self._running = True
+        self._thread = threading.Thread(target=body, name="luaradio_b200-scheduler", daemon=True)
+        self._thread.start()
+        return self
+
+    def status(self):
+        """{'running': bool} like composite.lua:858-877."""
+        return {"running": bool(getattr(self, "_running", False))}
+
+    def stop(self):
+        """Ask the scheduler to stop after the vector in flight, then wait for it (composite.lua:886-906)."""
+        if getattr(self, "_thread", None) is None:
+            return
+        self._stop_requested = True
+        self.wait()
+
+    def wait(self):
+        """Block until the flow graph has finished (sources at EOF or stop()); re-raises a block's error."""
+        t = getattr(self, "_thread", None)
+        if t is None:
+            return
+        t.join()
+        self._thread = None
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
+
+    def run(self, multiprocess=False, fuse=True, superchunk=0):
+        """start() + wait() (composite.lua:937-941), on the calling thread."""
+        if getattr(self, "_running", False):
+            raise RuntimeError("CompositeBlock already running!")
+        self._prepare_to_run()
+        self._stop_requested, self._error = False, None
+        self._running = True
+        try:
+            self._run_body(fuse, superchunk)
+        finally:
+            self._running = False
+        return self
+
+
+class GPUChainBlock(Block):
+    """A maximal linear run of connected GPU blocks as ONE device-resident flow graph (lrb200_graph_*): the executable
+    twin of lua/radio_b200/composite_patch.lua's GPUChainBlock.  An absorbed raw file source makes it a source block (the
+    file's own bytes cross PCIe and are converted by the graph's first stage), an absorbed raw file sink a sink block."""
+    name = "GPUChainBlock"
+    RAW_READ = 1 << 19          # samples per read when the chain pulls from an absorbed file source (the reference's 8192 is launch-bound)
+
+    def instantiate(self, blocks, raw_source=None, raw_sink=None, fuse=True, superchunk=0):
+        self.blocks, self.raw_source, self.raw_sink = list(blocks), raw_source, raw_sink
+        self.fuse, self.superchunk = fuse, int(superchunk or 0)
+        self.graph, self.desc = None, ""
+        ins = [] if raw_source is not None else [Input("in", blocks[0].get_input_type())]
+        outs = [] if raw_sink is not None else [Output("out", blocks[-1].get_output_type())]
+        self.add_type_signature(ins, outs)
+        self.differentiate([d.data_type for d in ins])
+
+    def get_rate(self):
+        return self.blocks[-1].get_rate()
+
+    def initialize(self):
+        lib = self._lib = _lib.require_device()
+        g = _lib.check_handle(lib.lrb200_graph_create(), "lrb200 graph")
+        self.graph = g
+        if self.raw_source is not None:
+            _lib.check(lib.lrb200_graph_append(g, self.raw_source.make_device_handle()), "graph_append(file source)")
+        for b in self.blocks:
+            _lib.check(lib.lrb200_graph_append(g, b.make_device_handle()), "graph_append(%s)" % b.name)
+        if self.raw_sink is not None:
+            _lib.check(lib.lrb200_graph_append(g, self.raw_sink.make_device_handle()), "graph_append(file sink)")
+        _lib.check(lib.lrb200_graph_commit(g, 1 if self.fuse else 0), "graph_commit")
+        self.desc = lib.lrb200_graph_describe(g).decode()
+        if self.superchunk:
+            _lib.check(lib.lrb200_graph_set_superchunk(g, self.superchunk), "graph_set_superchunk")
+        self.out = None if self.raw_sink is not None else self.blocks[-1].get_output_type().vector()
+        self._raw_out = np.zeros(0, np.uint8)
+        self._n_out = ctypes.c_size_t(0)
+
+    def _execute(self, in_ptr, n_in, flush=False):
+        lib, g = self._lib, self.graph
+        cap = lib.lrb200_graph_max_output(g, n_in)
+        if self.raw_sink is not None:
+            need = cap * self.raw_sink.raw_sample_bytes
+            if len(self._raw_out) < need:
+                self._raw_out = np.zeros(need, np.uint8)
+            out_ptr = self._raw_out.ctypes.data
+        else:
+            self.out.resize(cap)
+            out_ptr = self.out.ctypes_ptr()
+        if flush:
+            _lib.check(lib.lrb200_graph_flush(g, out_ptr, ctypes.byref(self._n_out)), "graph_flush")
+        else:
+            _lib.check(lib.lrb200_graph_execute(g, in_ptr, n_in, out_ptr, ctypes.byref(self._n_out)), "graph_execute")
+        n = self._n_out.value
+        if self.raw_sink is not None:
+            if n:
+                self.raw_sink.write_raw(self._raw_out[:n * self.raw_sink.raw_sample_bytes], n)
+            return None
+        return self.out.resize(n)
+
+    def process(self, x=None):
+        if self.raw_source is not None:
+            raw = self.raw_source.read_raw(max(self.raw_source.chunk_size, self.RAW_READ))
+            if raw is None:
+                return None                                   # EOF (block.lua:588)
+            r = self._execute(raw.ctypes.data, len(raw) // self.raw_source.sample_bytes)
+            return r if r is not None else ()
+        return self._execute(x.ctypes_ptr(), x.length)
+
+    def flush(self):
+        return self._execute(None, 0, flush=True) if self.graph else None
+
+    def cleanup(self):
+        if self.graph:
+            self._lib.lrb200_graph_destroy(self.graph)
+            self.graph = None
 
 
 # -------------------------------------------------------------------------------------------------
@@ -680,6 +867,72 @@ class SSBDemodulator(CompositeBlock):
         self.connect(sb_filter, am_demod, af_filter)
         self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
         self.connect(self, "in", sb_filter, "in")
+        self.connect(self, "out", af_filter, "out")
+
+
+class WBFMStereoDemodulator(CompositeBlock):
+    """composites/wbfmstereodemodulator.lua:22-64: discriminator -> Hilbert(129); pilot: ComplexBandpass(129, 18-20 kHz) ->
+    PLL(100, 19 kHz +- 50, x2); L+R: Delay(129) -> Lowpass(128, 15e3) -> ComplexToReal; L-R: Delay * conj(PLL) -> Lowpass ->
+    ComplexToReal; left = (L+R) + (L-R), right = (L+R) - (L-R), each -> FMDeemphasis(tau).  A DAG: the scheduler turns its
+    linear GPU runs (discriminator -> Hilbert; Lowpass -> ComplexToReal twice) into device flow graphs, the two-input
+    blocks and the PLL run as single GPU blocks at their junctions."""
+    name = "WBFMStereoDemodulator"
+
+    def instantiate(self, tau=None):
+        CompositeBlock.instantiate(self)
+        tau = tau or 75e-6
+        bandwidth = 15e3
+        fm_demod = FrequencyDiscriminatorBlock(1.25)
+        hilbert = HilbertTransformBlock(129)
+        delay = DelayBlock(129)
+        pilot_filter = ComplexBandpassFilterBlock(129, [18e3, 20e3])
+        pilot_pll = PLLBlock(100, 19e3 - 50, 19e3 + 50, 2)
+        mixer = MultiplyConjugateBlock()
+        lpr_filter, lpr_am_demod = LowpassFilterBlock(128, bandwidth), ComplexToRealBlock()
+        lmr_filter, lmr_am_demod = LowpassFilterBlock(128, bandwidth), ComplexToRealBlock()
+        l_sum, left_af_deemphasis = AddBlock(), FMDeemphasisFilterBlock(tau)
+        r_sub, right_af_deemphasis = SubtractBlock(), FMDeemphasisFilterBlock(tau)
+        self.connect(fm_demod, hilbert)
+        self.connect(hilbert, pilot_filter)
+        self.connect(pilot_filter, "out", pilot_pll, "in")
+        self.connect(hilbert, delay)
+        self.connect(delay, "out", mixer, "in1")
+        self.connect(pilot_pll, "out", mixer, "in2")
+        self.connect(delay, lpr_filter, lpr_am_demod)
+        self.connect(mixer, lmr_filter, lmr_am_demod)
+        self.connect(lpr_am_demod, "out", l_sum, "in1")
+        self.connect(lmr_am_demod, "out", l_sum, "in2")
+        self.connect(lpr_am_demod, "out", r_sub, "in1")
+        self.connect(lmr_am_demod, "out", r_sub, "in2")
+        self.connect(l_sum, left_af_deemphasis)
+        self.connect(r_sub, right_af_deemphasis)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("left", Float32), Output("right", Float32)])
+        self.connect(self, "in", fm_demod, "in")
+        self.connect(self, "left", left_af_deemphasis, "out")
+        self.connect(self, "right", right_af_deemphasis, "out")
+
+
+class AMSynchronousDemodulator(CompositeBlock):
+    """composites/amsynchronousdemodulator.lua:25-45: ComplexBandpass(129, ifreq +- bandwidth) -> [PLL(1000, ifreq +- 100)]
+    -> MultiplyConjugate(filtered, pll) -> ComplexToReal -> SinglepoleHighpass(100) -> Lowpass(128, bandwidth)."""
+    name = "AMSynchronousDemodulator"
+
+    def instantiate(self, ifreq, bandwidth=None):
+        CompositeBlock.instantiate(self)
+        assert ifreq is not None, "Missing argument #1 (ifreq)"
+        bandwidth = bandwidth or 5e3
+        rf_filter = ComplexBandpassFilterBlock(129, [ifreq - bandwidth, ifreq + bandwidth])
+        pll = PLLBlock(1000, ifreq - 100, ifreq + 100)
+        mixer = MultiplyConjugateBlock()
+        am_demod = ComplexToRealBlock()
+        dcr_filter = SinglepoleHighpassFilterBlock(100)
+        af_filter = LowpassFilterBlock(128, bandwidth)
+        self.connect(rf_filter, "out", pll, "in")
+        self.connect(rf_filter, "out", mixer, "in1")
+        self.connect(pll, "out", mixer, "in2")
+        self.connect(mixer, am_demod, dcr_filter, af_filter)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", Float32)])
+        self.connect(self, "in", rf_filter, "in")
         self.connect(self, "out", af_filter, "out")
 
 

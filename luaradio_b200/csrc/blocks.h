@@ -18,8 +18,18 @@ struct Block {
     virtual ~Block();
     virtual int init() { return 0; }
     virtual size_t max_output(size_t n) const { return n; }
+    int num_inputs = 1, num_outputs = 1;
     // device pointers in/out, asynchronous on s; consumes n, produces *n_out, advances the carried state
     virtual int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) = 0;
+    // blocks with several input / output ports (all inputs the same length n and element size in_size, block.lua:516-532)
+    virtual int run_multi(const void* const* dx, int nin, size_t n, void* const* dy, int nout, size_t* n_out, cudaStream_t s) {
+        if (nin != 1 || nout != 1) { set_error("%s has one input and one output", name); return -1; }
+        return run(dx[0], n, dy[0], n_out, s);
+    }
+    int execute_multi(const void* const* x, int nin, size_t n, void* const* y, int nout, size_t* n_out);
+    virtual size_t out_size_of(int port) const { (void)port; return out_size; }    // element size of output port `port`
+    std::vector<void*> m_bufs;        // host-mode staging of execute_multi: nin + nout device buffers
+    std::vector<size_t> m_caps;
     // reset = host-side bookkeeping + zeroing the device state buffers; a graph zeroes every stage's buffers with ONE
     // kernel (a 256 Mi-sample chain step is ~1 ms: a dozen cudaMemsetAsync nodes per step were 1.5 % of it)
     virtual void reset_host() { consumed = 0; }

@@ -63,6 +63,48 @@ static constexpr size_t HOST_CHUNK = (size_t)1 << 24;   // samples per staged ch
 Block::~Block() {
     cudaFree(d_in);
     cudaFree(d_out);
+    for (void* p : m_bufs) cudaFree(p);
+}
+
+int Block::execute_multi(const void* const* x, int nin, size_t n, void* const* y, int nout, size_t* n_out) {
+    cudaStream_t s = ctx().stream;
+    if (nin != num_inputs || nout != num_outputs) {
+        set_error("%s: expected %d input(s) and %d output(s), got %d and %d", name, num_inputs, num_outputs, nin, nout);
+        return -1;
+    }
+    size_t produced = 0;
+    if (dev_ptrs) {
+        if (run_multi(x, nin, n, y, nout, &produced, s) != 0) return -1;
+        if (n_out) *n_out = produced;
+        return 0;
+    }
+    if (m_bufs.empty()) { m_bufs.assign((size_t)(nin + nout), nullptr); m_caps.assign((size_t)(nin + nout), 0); }
+    size_t done = 0;
+    std::vector<const void*> din((size_t)nin);
+    std::vector<void*> dout((size_t)nout);
+    while (done < n || (n == 0 && done == 0)) {
+        const size_t nc = n - done < HOST_CHUNK ? n - done : HOST_CHUNK;
+        const size_t mo = max_output(nc);
+        for (int i = 0; i < nin; ++i) {
+            if (reserve(&m_bufs[(size_t)i], &m_caps[(size_t)i], (nc ? nc : 1) * in_size) != 0) return -1;
+            if (nc) LRB_CHECK(cudaMemcpyAsync(m_bufs[(size_t)i], (const char*)x[i] + done * in_size, nc * in_size, cudaMemcpyHostToDevice, s));
+            din[(size_t)i] = m_bufs[(size_t)i];
+        }
+        for (int o = 0; o < nout; ++o) {
+            if (reserve(&m_bufs[(size_t)(nin + o)], &m_caps[(size_t)(nin + o)], (mo ? mo : 1) * out_size_of(o)) != 0) return -1;
+            dout[(size_t)o] = m_bufs[(size_t)(nin + o)];
+        }
+        size_t no = 0;
+        if (run_multi(din.data(), nin, nc, dout.data(), nout, &no, s) != 0) return -1;
+        for (int o = 0; o < nout; ++o)
+            if (no) LRB_CHECK(cudaMemcpyAsync((char*)y[o] + produced * out_size_of(o), dout[(size_t)o], no * out_size_of(o), cudaMemcpyDeviceToHost, s));
+        LRB_CHECK(cudaStreamSynchronize(s));
+        produced += no;
+        done += nc;
+        if (n == 0) break;
+    }
+    if (n_out) *n_out = produced;
+    return 0;
 }
 
 int Block::reserve(void** p, size_t* cap, size_t bytes) {
@@ -532,6 +574,16 @@ int lrb200_block_execute(lrb200_block_t* q, const void* x, size_t n, void* y, si
     if (n > 0 && (!x || !y)) { set_error("%s: null sample buffer", q->impl->name); return -1; }
     return q->impl->execute(x, n, y, n_out);
 }
+int lrb200_block_execute_multi(lrb200_block_t* q, const void* const* x, unsigned num_inputs, size_t n, void* const* y,
+                               unsigned num_outputs, size_t* n_out) {
+    if (!q || !q->impl) { set_error("null block handle"); return -1; }
+    if (!x || !y) { set_error("%s: null port array", q->impl->name); return -1; }
+    for (unsigned i = 0; i < num_inputs; ++i) if (n > 0 && !x[i]) { set_error("%s: null sample buffer", q->impl->name); return -1; }
+    for (unsigned i = 0; i < num_outputs; ++i) if (n > 0 && !y[i]) { set_error("%s: null sample buffer", q->impl->name); return -1; }
+    return q->impl->execute_multi(x, (int)num_inputs, n, y, (int)num_outputs, n_out);
+}
+unsigned lrb200_block_num_inputs(const lrb200_block_t* q) { return q && q->impl ? (unsigned)q->impl->num_inputs : 0; }
+unsigned lrb200_block_num_outputs(const lrb200_block_t* q) { return q && q->impl ? (unsigned)q->impl->num_outputs : 0; }
 size_t lrb200_block_max_output(const lrb200_block_t* q, size_t n) { return q && q->impl ? q->impl->max_output(n) : 0; }
 size_t lrb200_block_in_size(const lrb200_block_t* q) { return q && q->impl ? q->impl->in_size : 0; }
 size_t lrb200_block_out_size(const lrb200_block_t* q) { return q && q->impl ? q->impl->out_size : 0; }

@@ -371,3 +371,98 @@ class UpsamplerBlock(GPUBlock):
     def _make_handle(self, flags):
         return _lib.check_handle(_lib.load().lrb200_upsample_create(self.factor, self.get_input_type().size, flags),
                                  "lrb200 upsampler object")
+
+
+# ---------------------------------------------------------------------------------------------
+# Blocks the WBFM-stereo / AM-synchronous chains add to the hot path
+# ---------------------------------------------------------------------------------------------
+class GPUMultiBlock(GPUBlock):
+    """A GPU block with several input and/or output ports: process(x1, x2, ...) -> (y1, y2, ...) through
+    lrb200_block_execute_multi.  All inputs have the same length (block.lua:516-532)."""
+    out_types = None              # data types of the output ports (default: the signature's)
+
+    def initialize(self):
+        lib = _lib.require_device()
+        self._lib = lib
+        self._handle = self._make_handle(_lib.LRB200_HOST)
+        self.outs = [self.get_output_type(i + 1).vector() for i in range(len(self.outputs))]
+
+    def process(self, *xs):
+        lib, n = self._lib, xs[0].length
+        cap = lib.lrb200_block_max_output(self._handle, n)
+        for o in self.outs:
+            o.resize(cap)
+        ins = (ctypes.c_void_p * len(xs))(*[x.ctypes_ptr() for x in xs])
+        outs = (ctypes.c_void_p * len(self.outs))(*[o.ctypes_ptr() for o in self.outs])
+        n_out = ctypes.c_size_t(0)
+        rc = lib.lrb200_block_execute_multi(self._handle, ins, len(xs), n, outs, len(self.outs), ctypes.byref(n_out))
+        if rc != 0:
+            raise _lib.LibraryError("%s: %s" % (self.name, _lib.last_error()))
+        res = tuple(o.resize(n_out.value) for o in self.outs)
+        return res[0] if len(res) == 1 else res
+
+
+class _BinaryBlock(GPUMultiBlock):
+    op = None
+    real_too = True
+
+    def instantiate(self):
+        self.add_type_signature([Input("in1", ComplexFloat32), Input("in2", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        if self.real_too:
+            self.add_type_signature([Input("in1", Float32), Input("in2", Float32)], [Output("out", Float32)])
+
+    def _make_handle(self, flags):
+        cplx = 1 if self.get_input_type() is ComplexFloat32 else 0
+        return _lib.check_handle(_lib.load().lrb200_binary_create(self.op.encode(), cplx, flags), "lrb200 %s object" % self.op)
+
+
+class MultiplyBlock(_BinaryBlock):
+    """multiply.lua:26-60: out = in1 * in2 (complex or real)."""
+    name, op = "MultiplyBlock", "multiply"
+
+
+class MultiplyConjugateBlock(_BinaryBlock):
+    """multiplyconjugate.lua:26-51: out = in1 * conj(in2)."""
+    name, op, real_too = "MultiplyConjugateBlock", "multiplyconjugate", False
+
+
+class AddBlock(_BinaryBlock):
+    """add.lua:23-60: out = in1 + in2."""
+    name, op = "AddBlock", "add"
+
+
+class SubtractBlock(_BinaryBlock):
+    """subtract.lua:23-60: out = in1 - in2."""
+    name, op = "SubtractBlock", "subtract"
+
+
+class DelayBlock(GPUBlock):
+    """delay.lua:26-60: out[n] = in[n - num_samples], zeros first (ComplexFloat32 / Float32)."""
+    name = "DelayBlock"
+
+    def instantiate(self, num_samples):
+        assert num_samples is not None, "Missing argument #1 (num_samples)"
+        assert num_samples > 0, "Number of samples must be greater than 0"
+        self.num_samples = int(num_samples)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+        self.add_type_signature([Input("in", Float32)], [Output("out", Float32)])
+
+    def _make_handle(self, flags):
+        return _lib.check_handle(_lib.load().lrb200_delay_create(self.num_samples, self.get_input_type().size, flags), "lrb200 delay object")
+
+
+class PLLBlock(GPUMultiBlock):
+    """pll.lua:27-170: in -> out (exp(j * multiplied phase)), error (phase detector output)."""
+    name = "PLLBlock"
+
+    def instantiate(self, loop_bandwidth, frequency_min, frequency_max, multiplier=None):
+        assert loop_bandwidth is not None, "Missing argument #1 (loop_bandwidth)"
+        assert frequency_min is not None, "Missing argument #2 (frequency_min)"
+        assert frequency_max is not None, "Missing argument #3 (frequency_max)"
+        self.loop_bw, self.freq_min, self.freq_max = float(loop_bandwidth), float(frequency_min), float(frequency_max)
+        self.multiplier = 1.0 if multiplier is None else float(multiplier)
+        self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32), Output("error", Float32)])
+
+    def _make_handle(self, flags):
+        return _lib.check_handle(_lib.load().lrb200_pll_create(self.loop_bw, self.freq_min, self.freq_max, self.multiplier, self.get_rate(), flags),
+                                 "lrb200 pll object")

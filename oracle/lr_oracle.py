@@ -393,6 +393,99 @@ def multiply_conjugate(x, y):
     return (np.asarray(x).astype(np.complex128) * np.conj(np.asarray(y).astype(np.complex128))).astype(C64)
 
 
+def binary_op(op, x, y):
+    """multiply.lua / add.lua / subtract.lua process bodies: element-wise on two equal-length vectors."""
+    x, y = np.asarray(x), np.asarray(y)
+    acc = np.complex128 if np.iscomplexobj(x) else np.float64
+    a, b = x.astype(acc), y.astype(acc)
+    r = {"multiply": a * b, "add": a + b, "subtract": a - b, "multiplyconjugate": a * np.conj(b)}[op]
+    return r.astype(C64 if np.iscomplexobj(x) else F32)
+
+
+class Delay:
+    """delay.lua:26-60: out[n] = in[n - num_samples], zeros first; the last num_samples inputs are carried."""
+
+    def __init__(self, num_samples):
+        self.D = int(num_samples)
+        self.state = None
+
+    def process(self, x):
+        x = np.asarray(x)
+        if self.state is None:
+            self.state = np.zeros(self.D, x.dtype)
+        cat = np.concatenate([self.state, x])
+        self.state = cat[len(cat) - self.D:]
+        return cat[:len(x)].astype(x.dtype)
+
+
+class PLL:
+    """pll.lua:113-170 restated operation by operation: Lua numbers are float64; the VCO output, the phase-detector
+    product (complexfloat32.lua:79-81) and the error (atan2f, :150-152) are float32 cells.  NOTE: the reference has no
+    pll_spec -- this block's parity is pinned only by this restatement (SURVEY.md 8c gaps)."""
+
+    def __init__(self, loop_bandwidth, frequency_min, frequency_max, multiplier, rate):
+        bw = 2 * math.pi * (loop_bandwidth / rate)
+        self.fmin = 2 * math.pi * (frequency_min / rate)
+        self.fmax = 2 * math.pi * (frequency_max / rate)
+        damping = math.sqrt(2) / 2
+        bw = bw / (damping + 1 / (4 * damping))
+        denom = 1 + 2 * damping * bw + bw * bw
+        self.alpha = (4 * damping * bw) / denom
+        self.beta = (4 * bw * bw) / denom
+        self.mult = 1.0 if multiplier is None else multiplier
+        self.phi = 0.0
+        self.phim = 0.0
+        self.freq = (self.fmin + self.fmax) / 2.0
+
+    def process(self, x):
+        x = np.asarray(x, C64)
+        out = np.zeros(len(x), C64)
+        err = np.zeros(len(x), F32)
+        two_pi = 2 * math.pi
+        phi, phim, freq = self.phi, self.phim, self.freq
+        for i in range(len(x)):
+            vr, vi = F32(math.cos(phi)), F32(math.sin(phi))
+            out[i] = complex(F32(math.cos(phim)), F32(math.sin(phim)))
+            xr, xi = float(x[i].real), float(x[i].imag)
+            pr = F32(xr * float(vr) - xi * float(-vi))
+            pi = F32(xr * float(-vi) + xi * float(vr))
+            e = float(np.arctan2(pi, pr, dtype=F32))
+            err[i] = e
+            freq = freq + self.beta * e
+            phi = phi + freq + self.alpha * e
+            phim = phim + freq * self.mult + self.alpha * e
+            freq = min(max(freq, self.fmin), self.fmax)
+            if phi > two_pi:
+                phi -= two_pi
+            if phi < -two_pi:
+                phi += two_pi
+            if phim > two_pi:
+                phim -= two_pi
+            if phim < -two_pi:
+                phim += two_pi
+        self.phi, self.phim, self.freq = phi, phim, freq
+        return out, err
+
+
+def psd(samples, window_type="hamming", sample_rate=2, logarithmic=True):
+    """spectrum_utils.lua:524-642 (PSD:compute, pure-Lua branch): periodic window as float32, DFT, |X_k|^2 / (rate *
+    window energy), optionally 10*log10."""
+    x = np.asarray(samples)
+    n = len(x)
+    w = np.array(window(n, window_type, True), F32)
+    energy = float(np.sum(w.astype(np.float64) ** 2))
+    if np.iscomplexobj(x):
+        xw = (x.astype(np.complex128) * w.astype(np.float64)).astype(C64)
+    else:
+        xw = (x.astype(np.float64) * w.astype(np.float64)).astype(F32)
+    X = np.fft.fft(xw.astype(np.complex128)).astype(C64)
+    p = (X.real.astype(np.float64) ** 2 + X.imag.astype(np.float64) ** 2) / (sample_rate * energy)
+    if logarithmic:
+        with np.errstate(divide="ignore"):
+            p = 10 * np.log10(p)
+    return p.astype(F32)
+
+
 # ----------------------------------------------------------------------------------------------
 # Filter wrappers (taps designed from get_rate() in initialize()) and composites
 # ----------------------------------------------------------------------------------------------

@@ -41,6 +41,7 @@ BLOCK_SPECS = [
     "composites/tuner_spec", "composites/decimator_spec",
     "blocks/signal/multiplyconstant_spec", "blocks/signal/upsampler_spec",
     "composites/interpolator_spec", "composites/rationalresampler_spec",
+    "blocks/signal/multiply_spec", "blocks/signal/add_spec", "blocks/signal/subtract_spec", "blocks/signal/delay_spec",
 ]
 MODULE_SPECS = ["utilities/filter_utils_vectors", "utilities/window_utils_vectors", "utilities/spectrum_utils_vectors"]
 

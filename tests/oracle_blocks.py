@@ -69,4 +69,9 @@ def make_oracle(block, args, inputs, rate=2.0):
     if block == "RationalResamplerBlock":
         o = opt(2, {}) or {}
         return O.rational_resampler(a[0], a[1], cin, o.get("num_taps", 128), o.get("window", "hamming"))
+    if block == "DelayBlock":
+        return O.Delay(a[0])
     raise KeyError(block)
+
+
+BINARY_OPS = {"MultiplyBlock": "multiply", "MultiplyConjugateBlock": "multiplyconjugate", "AddBlock": "add", "SubtractBlock": "subtract"}

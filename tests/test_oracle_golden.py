@@ -8,7 +8,8 @@ from oracle import lr_oracle as O
 from tests.golden_util import all_block_specs, epsilon_ok, load_spec, GOLDEN_DIR
 from tests.oracle_blocks import make_oracle
 
-SPECS = [s for s in all_block_specs() if s != "multiplyconjugate_spec"]
+TWO_INPUT = ("multiplyconjugate_spec", "multiply_spec", "add_spec", "subtract_spec")
+SPECS = [s for s in all_block_specs() if s not in TWO_INPUT]
 
 
 @pytest.mark.parametrize("spec", SPECS)
@@ -38,6 +39,28 @@ def test_oracle_multiply_conjugate():
     for v in vectors:
         ok, msg = epsilon_ok(O.multiply_conjugate(*v["inputs"]), v["outputs"][0], eps)
         assert ok, msg
+
+
+@pytest.mark.parametrize("spec", TWO_INPUT)
+def test_oracle_two_input_blocks(spec):
+    from tests.oracle_blocks import BINARY_OPS
+    block, vectors, eps = load_spec(spec)
+    for v in vectors:
+        ok, msg = epsilon_ok(O.binary_op(BINARY_OPS[block], *v["inputs"]), v["outputs"][0], eps)
+        assert ok, "%s / %s: %s" % (block, v["desc"], msg)
+
+
+def test_oracle_psd_vectors():
+    """tests/utilities/spectrum_utils_spec.lua:58-72: PSD of the committed test vectors, rectangular and hamming, linear at
+    1e-5 and logarithmic within 3 (dB), exactly the reference's tolerances."""
+    z = np.load(GOLDEN_DIR + "/spectrum_utils_vectors.npz")
+    for kind in ("complex", "real"):
+        x = z[kind + "_test_vector"]
+        for win in ("rectangular", "hamming"):
+            ok, msg = epsilon_ok(O.psd(x, win, 44100, False), z["%s_test_vector_%s_psd" % (kind, win)], 1e-5)
+            assert ok, (kind, win, msg)
+            ok, msg = epsilon_ok(O.psd(x, win, 44100, True), z["%s_test_vector_%s_psd_log" % (kind, win)], 3)
+            assert ok, (kind, win, "log", msg)
 
 
 def test_oracle_tap_design():
