@@ -447,19 +447,24 @@ def run_b200(args):
 
 def bench_e2e_small(lib, _lib, g, hin_pinned, n_avail):
     """The drop-in regime: lrb200_graph_execute on PAGEABLE host vectors of the sizes the reference's pipes deliver."""
-    out = {"unit": "Msamples/s", "memory": "pageable (numpy) in and out", "api": "lrb200_graph_execute",
-           "sync": {}, "superchunk_1Mi": {}}
+    out = {"unit": "Msamples/s", "memory": "pageable (numpy) in and out; sync_pinned: vectors in lrb200_host_alloc memory "
+                                          "(what a platform.alloc hook gives the reference's pipe buffers, INTEGRATION.md)",
+           "api": "lrb200_graph_execute", "sync": {}, "superchunk_1Mi": {}, "sync_pinned": {}}
     src = np.ctypeslib.as_array(ctypes.cast(hin_pinned, ctypes.POINTER(ctypes.c_float)), shape=(2 * n_avail,))
     for vec, total in ((8192, 1 << 25), (32768, 1 << 26), (131072, 1 << 27)):
         total = min(total, (n_avail // vec) * vec)
         x = np.array(src[:2 * total], copy=True)             # pageable copy of the stream
-        for mode, sc in (("sync", 0), ("superchunk_1Mi", 1 << 20)):
+        for mode, sc in (("sync", 0), ("superchunk_1Mi", 1 << 20), ("sync_pinned", 0)):
             _lib.check(lib.lrb200_graph_reset(g), "reset")
             _lib.check(lib.lrb200_graph_set_superchunk(g, sc), "set_superchunk")
             cap = lib.lrb200_graph_max_output(g, vec) + 64
             y = np.empty(cap, np.float32)
             no = ctypes.c_size_t(0)
             xp, yp = x.ctypes.data, y.ctypes.data
+            ypin = None
+            if mode == "sync_pinned":
+                ypin = lib.lrb200_host_alloc(cap * 4)
+                xp, yp = hin_pinned, ypin
             produced = 0
             for o in range(0, 64 * vec, vec):                 # warm-up
                 _lib.check(lib.lrb200_graph_execute(g, xp + o * 8, vec, yp, ctypes.byref(no)), "execute")
@@ -476,6 +481,8 @@ def bench_e2e_small(lib, _lib, g, hin_pinned, n_avail):
             el = time.perf_counter() - t0
             assert produced == (total + 24) // 25, (produced, total)
             out[mode][str(vec)] = round(total / el / 1e6, 1)
+            if ypin:
+                lib.lrb200_host_free(ypin)
         del x
     _lib.check(lib.lrb200_graph_set_superchunk(g, 0), "set_superchunk")
     _lib.check(lib.lrb200_graph_reset(g), "reset")

@@ -497,9 +497,10 @@ class CompositeBlock(Block):
         """Rewrite (self._all_connections, self._concrete_order): every maximal linear run of GPU blocks becomes one
         GPUChainBlock (a run of one block keeps the block's own handle unless it borders a raw file source / sink); a raw
         file source feeding only the run, and a raw file sink fed only by it, are absorbed as its first / last stage."""
-        conns = dict(self._all_connections)
+        orig = self._all_connections          # lookups use the untouched map; the rewrite goes into `conns`
+        conns = dict(orig)
         consumers = {}
-        for inp, outp in conns.items():
+        for inp, outp in orig.items():
             consumers.setdefault(outp, []).append(inp)
 
         def is_gpu(b):
@@ -510,7 +511,7 @@ class CompositeBlock(Block):
             return c[0].owner if len(c) == 1 and is_gpu(c[0].owner) else None
 
         def prev_in_run(b):
-            up = conns[b.inputs[0]].owner
+            up = orig[b.inputs[0]].owner
             return up if is_gpu(up) and next_in_run(up) is b else None
 
         chains = []
@@ -521,7 +522,7 @@ class CompositeBlock(Block):
             while nb is not None:
                 run.append(nb)
                 nb = next_in_run(nb)
-            up_port = conns[run[0].inputs[0]]
+            up_port = orig[run[0].inputs[0]]
             src = up_port.owner if getattr(up_port.owner, "raw_source", False) and len(consumers.get(up_port, [])) == 1 else None
             down = consumers.get(run[-1].outputs[0], [])
             snk = down[0].owner if len(down) == 1 and getattr(down[0].owner, "raw_sink", False) and len(down[0].owner.inputs) == 1 else None

@@ -64,6 +64,7 @@ struct FirBlock : Block {
     uint64_t rot_fix = 0;
     FirFast* fast = nullptr;
     PolyTaps* poly = nullptr;
+    bool gen_poly = false;            // poly_generic.cu covers this (kind, M, D)
     std::string label;                // owns `name` when a graph rewrite renames the block
     // output-rate pole fused behind a real polyphase decimator (graph rewrite of FIR -> IIR1 -> Downsampler)
     bool has_pole = false;

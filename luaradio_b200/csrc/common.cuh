@@ -60,6 +60,12 @@ int launch_fir_generic(FirKind kind, const void* x, const void* hist, const void
 int launch_hist_update(const void* x, long long n, const void* hist_old, void* hist_new, int H,
                        int elem_size, cudaStream_t s);
 
+// ---- poly_generic.cu --------------------------------------------------------------------------
+// register-tiled polyphase decimating FIR for any covered (kind, M, D); taps_host in natural order
+bool poly_generic_supports(FirKind kind, int M, int D);
+int launch_poly_generic(FirKind kind, const void* x, const void* hist, const void* taps_host, int M, int D,
+                        long long first, long long n, long long n_out, void* y, cudaStream_t s);
+
 // ---- elementwise.cu ---------------------------------------------------------------------------
 int launch_rotator(const float2* x, float2* y, long long n, uint64_t turns_fix, uint64_t g0, cudaStream_t s);
 int launch_discrim(const float2* x, const float2* prev, float* y, long long n, float inv_gain, cudaStream_t s);

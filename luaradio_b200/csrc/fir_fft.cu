@@ -543,6 +543,7 @@ int FirBlock::fast_init() {
     // register-tiled direct kernel: decimators with <= 128 taps and plain FIRs with <= 32 taps (complex in, real taps)
     if (kind == FIR_CRCF && !rotate) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0);
     if (kind == FIR_RRRF && D > 1) poly = polyphase_prepare((const float*)h_taps.data(), M, D, 0.0, false, true);
+    gen_poly = !rotate && D >= 2 && poly_generic_supports(kind, M, D);
     if (kind == FIR_HILBERT && D != 1) return 0;
     const bool long_filter = M > FFT_MAX_TAPS;
     // long filters: complex-input, no fused decimation/translator -> P partitions of 512 taps, P passes over x
@@ -619,9 +620,10 @@ int FirBlock::effective_algorithm() const {
     if (poly) return LRB200_FIR_DIRECT;                        // register-tiled polyphase decimator
     // automatic: overlap-save once the direct form would be FP32-bound.  Packed FFMA2 per INPUT sample:
     //   direct = M/D (crcf), 2M/D (cccf), M/2D (rrrf, hilbert);  overlap-save ~ 31 / (L/N) (half for packed real blocks)
-    // The only direct kernel for these shapes is the catch-all (about 8x off its FP32 bound), hence the factor.
-    const double per_tap = kind == FIR_CCCF ? 2.0 : (kind == FIR_CRCF ? 1.0 : 0.5);
-    const double direct_cost = 8.0 * per_tap * M / D;
+    // Direct kernels for these shapes: the generic polyphase kernel (about 2x off its FP32 bound; scalar FFMA for real
+    // streams) where it covers the shape, else the catch-all (about 8x off), hence the factors.
+    const double per_tap = kind == FIR_CCCF ? 2.0 : (kind == FIR_CRCF ? 1.0 : (gen_poly ? 1.0 : 0.5));
+    const double direct_cost = (gen_poly ? 2.0 : 8.0) * per_tap * M / D;
     const int mp = fast->part_taps;
     const double fft_cost = fast->nparts * 31.0 * FF_N / (double)(FF_N - mp + 1) * (kind == FIR_RRRF ? 0.5 : 1.0);
     return direct_cost > fft_cost ? LRB200_FIR_FFT : LRB200_FIR_DIRECT;
@@ -641,7 +643,12 @@ int FirBlock::fast_run(const void* dx, size_t n, void* dy, long long first, long
     if (poly && algo != LRB200_FIR_FFT)
         return launch_polyphase_crcf(poly, (const float2*)dx, (const float2*)d_hist[cur], (long long)n, (float2*)dy,
                                      first, n_out, false, 0, consumed, s);
-    if (!fast || effective_algorithm() != LRB200_FIR_FFT) {
+    const int eff = effective_algorithm();
+    if (gen_poly && eff == LRB200_FIR_DIRECT) {
+        const int rc = launch_poly_generic(kind, dx, d_hist[cur], h_taps.data(), M, D, first, (long long)n, n_out, dy, s);
+        if (rc != 0) return rc;
+    }
+    if (!fast || eff != LRB200_FIR_FFT) {
         if (rotate) { set_error("fir: fused translator needs the overlap-save path (ntaps <= %d)", FFT_MAX_TAPS); return -1; }
         return 0;
     }
