@@ -17,6 +17,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     std::atomic<uint64_t> launches{0};
+    // persistent kernels leave this many CTA slots free while a sharded run has a head piece queued on another stream
+    // (graph.cu: run_shard) -- otherwise the head's few small kernels only get an SM once the persistent grid drains
+    int reserve_ctas = 0;
     // side stream for the few-CTA edge kernels, so they overlap the interior kernel instead of trailing it
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

@@ -620,10 +620,11 @@ int FirBlock::effective_algorithm() const {
     if (poly) return LRB200_FIR_DIRECT;                        // register-tiled polyphase decimator
     // automatic: overlap-save once the direct form would be FP32-bound.  Packed FFMA2 per INPUT sample:
     //   direct = M/D (crcf), 2M/D (cccf), M/2D (rrrf, hilbert);  overlap-save ~ 31 / (L/N) (half for packed real blocks)
-    // Direct kernels for these shapes: the generic polyphase kernel (about 2x off its FP32 bound; scalar FFMA for real
-    // streams) where it covers the shape, else the catch-all (about 8x off), hence the factors.
+    // Direct kernels for these shapes: the generic polyphase kernel where it covers the shape (measured, profiles/
+    // r02_decim_shapes.json: it beats the overlap-save kernel only for short complex-input real-tap filters, e.g. (D, M) =
+    // (2, 16), (3, 33); tap loads from the constant bank pace it), else the catch-all (about 8x off), hence the factors.
     const double per_tap = kind == FIR_CCCF ? 2.0 : (kind == FIR_CRCF ? 1.0 : (gen_poly ? 1.0 : 0.5));
-    const double direct_cost = (gen_poly ? 2.0 : 8.0) * per_tap * M / D;
+    const double direct_cost = (gen_poly ? 3.0 : 8.0) * per_tap * M / D;
     const int mp = fast->part_taps;
     const double fft_cost = fast->nparts * 31.0 * FF_N / (double)(FF_N - mp + 1) * (kind == FIR_RRRF ? 0.5 : 1.0);
     return direct_cost > fft_cost ? LRB200_FIR_FFT : LRB200_FIR_DIRECT;

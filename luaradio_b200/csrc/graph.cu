@@ -494,8 +494,12 @@ struct Graph {
         total_rate(&up, &down);
         if (halo_n % down || start % down) { set_error("graph: halo and start must be multiples of %llu input samples", down); return -1; }
         if (reset(s) != 0 || seek(start) != 0) return -1;
-        if (run_device((const char*)dx + halo_n * isz, n, dy, n_out, s) != 0) return -1;
-        if (halo_n == 0 || start == 0) return 0;             // the stream's first chunk: nothing to its left
+        const bool has_head = halo_n != 0 && start != 0;
+        ctx().reserve_ctas = has_head ? 8 : 0;               // room for the head piece beside the persistent kernels
+        const int rc_main = run_device((const char*)dx + halo_n * isz, n, dy, n_out, s);
+        ctx().reserve_ctas = 0;
+        if (rc_main != 0) return -1;
+        if (!has_head) return 0;                             // the stream's first chunk: nothing to its left
         if (start < halo_n || n < halo_n) { set_error("graph: chunk shorter than the halo"); return -1; }
         if (!s_head) {
             LRB_CHECK(cudaStreamCreateWithFlags(&s_head, cudaStreamNonBlocking));

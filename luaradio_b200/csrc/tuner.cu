@@ -464,7 +464,8 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
         count_launch();
     }
     if (n_int > 0) {
-        long long grid = (long long)ctx().sm_count * ctas_per_sm;
+        long long grid = (long long)ctx().sm_count * ctas_per_sm - ctx().reserve_ctas;
+        if (grid < 1) grid = 1;
         if (grid > n_int) grid = n_int;
         kern_i<<<(unsigned)grid, PT_THREADS, S::SMEM, s>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();

@@ -249,13 +249,16 @@ def test_wbfm_stereo_demodulator_dag():
     ref_l = O.IIRFilterFast(b, a, False).process(O.binary_op("add", lpr, lmr))
     ref_r = O.IIRFilterFast(b, a, False).process(O.binary_op("subtract", lpr, lmr))
     # While the PLL ACQUIRES (phase detector near +-pi: an unstable equilibrium) 1e-7 differences in its input are
-    # amplified, so the comparison is loose there and tight once the loop is locked (the loop then contracts them).
+    # amplified, so the comparison is loose there.  Once locked the loop contracts differences in phi_locked, but the
+    # MULTIPLIED phase keeps them: phi_multiplied - 2 phi_locked = -alpha * sum of ALL past phase errors (pll.lua:155-157),
+    # so what the acquisition amplified stays as a constant phase offset of the 38 kHz carrier (measured: 3e-4 rad ->
+    # 7e-5 in the L-R path).  Hence 5e-4 when locked; the PLL alone is compared at 2e-5 on a clean pilot above.
     lock = 60000
     for got, ref in ((sl.result(), ref_l), (sr.result(), ref_r)):
         assert got.shape == ref.shape
         d = np.abs(got - ref)
         assert float(d[:lock].max()) <= 5e-3, "acquisition: max err %.3g at %d" % (float(d[:lock].max()), int(d[:lock].argmax()))
-        assert float(d[lock:].max()) <= 5e-5, "locked: max err %.3g at %d" % (float(d[lock:].max()), lock + int(d[lock:].argmax()))
+        assert float(d[lock:].max()) <= 5e-4, "locked: max err %.3g at %d" % (float(d[lock:].max()), lock + int(d[lock:].argmax()))
     # it separates the channels: after lock, left carries the 700 Hz tone and not the 2300 Hz one
     got_l = sl.result()[60000:]
     spec = np.abs(np.fft.rfft(got_l * np.hanning(len(got_l))))
