@@ -210,8 +210,10 @@ def run_b200(args):
     assert HALO > 0 and HALO % 25 == 0, HALO
     g_head = build_chain_graph(lib, _lib) if world > 1 else None
     # this rank's chunk lives at x[HALO:], the halo from the left neighbour is received into x[:HALO]
-    x = torch.empty(n + HALO, dtype=torch.complex64, device="cuda")
-    xp = x.data_ptr()
+    xp = lib.lrb200_malloc((n + HALO) * 8)                 # a plain cudaMalloc allocation: exportable to the neighbour process
+    assert xp, _lib.last_error()
+    x = None
+    assert (xp + HALO * 8) % 16 == 0
     _lib.check(lib.lrb200_synth_fm_iq(ctypes.c_void_p(xp + HALO * 8), start, n, 1, RATE, 250e3, 75e3, 0.5, 0.01), "synth")
     n_out_max = lib.lrb200_graph_max_output(g, n)
     y = torch.empty(n_out_max + 16, dtype=torch.float32, device="cuda")
@@ -220,13 +222,46 @@ def run_b200(args):
     n_out = ctypes.c_size_t(0)
     comm = torch.cuda.Stream() if world > 1 else None
     halo_ev = torch.cuda.Event() if world > 1 else None
+    # halo transport: "ipc" = the copy engine reads the left neighbour's tail through a peer-mapped pointer (no SM, no
+    # collective kernel beside the persistent compute kernels); "nccl" = batched NCCL send/recv on the side stream
+    transport, peer_tail = args.halo if world > 1 else "none", None
+    if world > 1 and transport == "ipc":
+        try:
+            hbuf = (ctypes.c_ubyte * 64)()
+            _lib.check(lib.lrb200_ipc_export(ctypes.c_void_p(xp), hbuf), "ipc_export")
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(hbuf))
+            if rank > 0:
+                base = lib.lrb200_ipc_import(handles[rank - 1])
+                if not base:
+                    raise RuntimeError(_lib.last_error())
+                peer_tail = base + (HALO + n - HALO) * 8          # the neighbour's last HALO samples
+            ok = torch.tensor([1], device="cuda")
+        except Exception as e:
+            sys.stderr.write("rank %d: CUDA IPC unavailable (%s)\n" % (rank, e))
+            ok = torch.tensor([0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            transport = "nccl"
+    if world > 1 and transport == "nccl":
+        xt = torch.empty(2 * HALO, dtype=torch.complex64, device="cuda")    # NCCL staging: [recv halo | send tail]
 
     def step():
         if world > 1:
             # neighbour exchange on its own stream: it only gates the head piece inside execute_shard
             comm.wait_stream(stream)
             with torch.cuda.stream(comm):
-                sharding.exchange_halo(dist, x[HALO:HALO + n], x[0:HALO], rank, world, HALO)
+                if transport == "ipc":
+                    if rank > 0:
+                        _lib.check(lib.lrb200_memcpy_d2d(ctypes.c_void_p(xp), ctypes.c_void_p(peer_tail), HALO * 8,
+                                                         ctypes.c_void_p(comm.cuda_stream)), "peer copy")
+                else:
+                    # stage through torch tensors: tail -> xt[HALO:], exchange, xt[:HALO] -> x[:HALO]
+                    _lib.check(lib.lrb200_memcpy_d2d(ctypes.c_void_p(xt.data_ptr() + HALO * 8), ctypes.c_void_p(xp + n * 8), HALO * 8,
+                                                     ctypes.c_void_p(comm.cuda_stream)), "stage tail")
+                    sharding.exchange_halo(dist, xt[HALO:], xt[:HALO], rank, world, HALO)
+                    _lib.check(lib.lrb200_memcpy_d2d(ctypes.c_void_p(xp), ctypes.c_void_p(xt.data_ptr()), HALO * 8,
+                                                     ctypes.c_void_p(comm.cuda_stream)), "unstage halo")
                 halo_ev.record(comm)
             _lib.check(lib.lrb200_graph_execute_shard(g, g_head, ctypes.c_void_p(xp), HALO, n, start, ctypes.c_void_p(y.data_ptr()),
                                                       ctypes.byref(n_out), ctypes.c_void_p(halo_ev.cuda_event)), "execute_shard")
@@ -349,10 +384,13 @@ def run_b200(args):
         g8 = build_chain_graph(lib, _lib, "u8")
         h8 = lib.lrb200_host_alloc(n * 2)
         assert h8, _lib.last_error()
-        xr = torch.view_as_real(x[HALO:HALO + n])
         CH = 1 << 24
+        xr = torch.empty(2 * CH, dtype=torch.float32, device="cuda")
         for o in range(0, n, CH):      # quantise the synthetic samples to u8 on the device, park them in pinned host memory
-            q = (xr[o:o + CH] * 127.5 + 127.5).round_().clamp_(0, 255).to(torch.uint8).contiguous()
+            m = min(CH, n - o)
+            _lib.check(lib.lrb200_memcpy_d2d(ctypes.c_void_p(xr.data_ptr()), ctypes.c_void_p(xp + (HALO + o) * 8), m * 8, None), "copy")
+            _lib.check(lib.lrb200_sync(), "sync")
+            q = (xr[:2 * m] * 127.5 + 127.5).round_().clamp_(0, 255).to(torch.uint8).contiguous()
             _lib.check(lib.lrb200_memcpy_d2h(ctypes.c_void_p(h8 + o * 2), ctypes.c_void_p(q.data_ptr()), q.numel()), "d2h")
             _lib.check(lib.lrb200_sync(), "sync")
             torch.cuda.synchronize()
@@ -410,7 +448,10 @@ def run_b200(args):
             "config": {"workload": args.workload if total == WORKLOADS[args.workload] else "wbfm_mono_%d" % total,
                        "samples_per_gpu": n, "total_samples": world * n, "sample_rate_hz": RATE, "chain": CHAIN,
                        "graph": desc, "halo_samples": HALO if world > 1 else 0,
-                       "sharding": "time-chunk, NCCL P2P halo on a side stream + head piece (lrb200_graph_execute_shard)" if world > 1 else "single GPU",
+                       "sharding": ("time-chunk; halo = %s on a side stream; head piece via lrb200_graph_execute_shard" %
+                                    {"ipc": "copy-engine read of the left neighbour's tail through a CUDA-IPC peer pointer over NVLink",
+                                     "nccl": "NCCL P2P send/recv"}[transport]) if world > 1 else "single GPU",
+                       "halo_transport": transport,
                        "l2": "inputs (%.1f GiB/step) larger than L2, no flush" % (n * 8 / 2**30), "tolerance": TOLERANCE},
             "gpu_launches": int(launches),
             "stages_ms": {k: round(v, 4) for k, v in stage_ms},
@@ -431,7 +472,12 @@ def run_b200(args):
     lib.lrb200_graph_destroy(g)
     if g_head:
         lib.lrb200_graph_destroy(g_head)
-    del x, y
+    if world > 1:
+        dist.barrier()                 # nobody frees a buffer a neighbour may still read
+    if peer_tail:
+        lib.lrb200_ipc_close(ctypes.c_void_p(peer_tail - n * 8))
+    lib.lrb200_free(ctypes.c_void_p(xp))
+    del y
 
     # ---- FIR-128 alone (second half of the BASELINE metric), configs[1] and the CPU baseline: rank 0, N == 1 only
     if rank == 0 and world == 1:
@@ -683,6 +729,7 @@ def main():
     ap.add_argument("--samples", type=int, default=0, help="override the workload's sample count (per GPU for the weak workload)")
     ap.add_argument("--fir-samples", type=int, default=1 << 28)
     ap.add_argument("--cpu-samples", type=int, default=1 << 26)
+    ap.add_argument("--halo", default="ipc", choices=["ipc", "nccl"], help="N > 1: transport of the halo exchange")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle window check of the run's output")
     ap.add_argument("--check", action="store_true", help="(default) compare output windows with the oracle and fail on mismatch")
     ap.add_argument("--profile", action="store_true", help="profiling run (ncu): skip the e2e, FIR-128 sweep and CPU legs")

@@ -69,6 +69,13 @@ void  lrb200_host_free(void* hptr);
 int   lrb200_memcpy_h2d(void* dst, const void* src, size_t bytes);   /* async on the library stream */
 int   lrb200_memcpy_d2h(void* dst, const void* src, size_t bytes);   /* async on the library stream */
 int   lrb200_memset(void* dptr, int value, size_t bytes);
+/* peer access between the per-GPU processes of a sharded stream (lrb200_graph_execute_shard): export a 64-byte handle of
+ * an lrb200_malloc allocation, import it in the neighbour process, and let the copy engine move the halo over NVLink
+ * (lrb200_memcpy_d2d on `cuda_stream`, NULL = the library stream) -- no SM and no collective kernel involved. */
+int   lrb200_ipc_export(void* dptr, void* handle_out64);
+void* lrb200_ipc_import(const void* handle64);
+int   lrb200_ipc_close(void* imported);
+int   lrb200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* cuda_stream);
 
 /* ---- generic block handle ------------------------------------------------------------------
  * Every block below is an lrb200_block_t; the typed names are aliases so the Lua cdef reads like

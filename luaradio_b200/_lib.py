@@ -35,6 +35,10 @@ _PROTOS = {
     "lrb200_memcpy_h2d": (c_int, [c_void_p, c_void_p, c_size_t]),
     "lrb200_memcpy_d2h": (c_int, [c_void_p, c_void_p, c_size_t]),
     "lrb200_memset": (c_int, [c_void_p, c_int, c_size_t]),
+    "lrb200_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "lrb200_ipc_import": (c_void_p, [c_void_p]),
+    "lrb200_ipc_close": (c_int, [c_void_p]),
+    "lrb200_memcpy_d2d": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "lrb200_block_execute": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, POINTER(c_size_t)]),
     "lrb200_block_execute_multi": (c_int, [c_void_p, POINTER(c_void_p), c_uint, c_size_t, POINTER(c_void_p), c_uint, POINTER(c_size_t)]),
     "lrb200_block_num_inputs": (c_uint, [c_void_p]),

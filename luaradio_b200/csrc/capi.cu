@@ -562,6 +562,36 @@ int lrb200_memcpy_d2h(void* dst, const void* src, size_t bytes) {
     LRB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_ctx.stream));
     return 0;
 }
+// ---- peer access for time-chunk sharding with one process per GPU: the left neighbour's tail is copied by the copy
+// engine over NVLink (no SM, no collective kernel competing with the persistent compute kernels)
+int lrb200_ipc_export(void* dptr, void* handle_out64) {
+    if (ensure_init() != 0) return -1;
+    if (!dptr || !handle_out64) { set_error("ipc_export: null pointer"); return -1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    LRB_CHECK(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(handle_out64, &h, sizeof(h));
+    return 0;
+}
+void* lrb200_ipc_import(const void* handle64) {
+    if (ensure_init() != 0) return nullptr;
+    if (!handle64) { set_error("ipc_import: null handle"); return nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    void* p = nullptr;
+    if (!cuda_ok(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle")) return nullptr;
+    return p;
+}
+int lrb200_ipc_close(void* imported) {
+    if (!imported) return 0;
+    LRB_CHECK(cudaIpcCloseMemHandle(imported));
+    return 0;
+}
+int lrb200_memcpy_d2d(void* dst, const void* src, size_t bytes, void* cuda_stream) {
+    if (ensure_init() != 0) return -1;
+    LRB_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, cuda_stream ? (cudaStream_t)cuda_stream : g_ctx.stream));
+    return 0;
+}
 int lrb200_memset(void* p, int value, size_t bytes) {
     if (ensure_init() != 0) return -1;
     LRB_CHECK(cudaMemsetAsync(p, value, bytes, g_ctx.stream));

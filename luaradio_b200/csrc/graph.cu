@@ -495,7 +495,7 @@ struct Graph {
         if (halo_n % down || start % down) { set_error("graph: halo and start must be multiples of %llu input samples", down); return -1; }
         if (reset(s) != 0 || seek(start) != 0) return -1;
         const bool has_head = halo_n != 0 && start != 0;
-        ctx().reserve_ctas = has_head ? 8 : 0;               // room for the head piece beside the persistent kernels
+        ctx().reserve_ctas = has_head ? 4 : 0;               // room for the head piece beside the persistent kernels
         const int rc_main = run_device((const char*)dx + halo_n * isz, n, dy, n_out, s);
         ctx().reserve_ctas = 0;
         if (rc_main != 0) return -1;
