@@ -53,8 +53,11 @@ namespace {
 #define LRB_PT_THREADS 128
 #define LRB_PT_R 8
 #define LRB_PT_CTAS 4
-#define LRB_PT_PREFETCH 7
+#define LRB_PT_PREFETCH 9
 #define LRB_PT_BATCH 7
+#endif
+#ifndef LRB_PT_EARLY_REST
+#define LRB_PT_EARLY_REST 0
 #endif
 constexpr int PT_THREADS = LRB_PT_THREADS;
 constexpr int PT_R = LRB_PT_R;
@@ -73,7 +76,10 @@ struct PolyParams {
     float pole_c;                // POLE: the output-rate pole c (z[m] = c z[m-1] + w[m])
     float pole_cp[6];            // c^(R * 2^k), k < 5; c^(R * 32)
 };
-constexpr int PT_POLE_WARM = 64; // POLE: outputs of warm-up in front of every run (|c|^64 <= 1e-8 is required by the host)
+// POLE: outputs of warm-up in front of every run (|c|^PT_POLE_WARM <= 1e-8 is required by the host); a whole number of
+// threads' outputs and a multiple of 4 (16-byte aligned stores)
+constexpr int PT_POLE_WARM = (64 % LRB_PT_R == 0) ? 64 : ((72 % LRB_PT_R == 0) ? 72 : 4 * LRB_PT_R);
+static_assert(PT_POLE_WARM % LRB_PT_R == 0 && PT_POLE_WARM % 4 == 0 && PT_POLE_WARM >= 64, "pole warm-up must cover whole threads");
 
 template <int D, int Q>
 struct PolyShape {
@@ -160,11 +166,20 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         }
     };
     float4 pre[NPRE];
+    // the next REST pairs: requested before the EPILOGUE of the previous tile (LRB_PT_EARLY_REST), so that their latency
+    // hides behind the epilogue's dependent chains instead of being exposed at the top of the staging phase (ncu, round 2:
+    // 44 % of the stall samples sat in the staging / epilogue regions, mostly long-scoreboard waits on these loads)
+    constexpr int REST = (S::ITERS - NPRE) < PT_BATCH ? (S::ITERS - NPRE) : PT_BATCH;
+    float4 rest[REST > 0 ? REST : 1];
     if constexpr (!EDGE) {
         if (widx < n_work) {
             const long long Bt = P.off + tile_of(widx) * (long long)(TS * D);
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) pre[k] = ld_pair(Bt, k);
+            if constexpr (LRB_PT_EARLY_REST) {
+#pragma unroll
+                for (int k = 0; k < REST; ++k) rest[k] = ld_pair(Bt, NPRE + k);
+            }
         }
     }
 
@@ -188,10 +203,10 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
         if constexpr (!EDGE) {
             // the first NPRE pairs were prefetched during the previous tile's compute phase; the rest of the tile
             // is requested now and lands while those are rotated and stored
-            constexpr int REST = (S::ITERS - NPRE) < PT_BATCH ? (S::ITERS - NPRE) : PT_BATCH;
-            float4 rest[REST > 0 ? REST : 1];
+            if constexpr (!LRB_PT_EARLY_REST) {
 #pragma unroll
-            for (int k = 0; k < REST; ++k) rest[k] = ld_pair(B, NPRE + k);
+                for (int k = 0; k < REST; ++k) rest[k] = ld_pair(B, NPRE + k);
+            }
 #pragma unroll
             for (int k = 0; k < NPRE; ++k) stage_pair(pre[k], k);
 #pragma unroll
@@ -278,6 +293,14 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 }
             });
         });
+        if constexpr (!EDGE && LRB_PT_EARLY_REST) {
+            const long long nidx = widx + gridDim.x;
+            if (nidx < n_work) {
+                const long long Bn = P.off + tile_of(nidx) * (long long)(TS * D);
+#pragma unroll
+                for (int k = 0; k < REST; ++k) rest[k] = ld_pair(Bn, NPRE + k);
+            }
+        }
         // tile phasor: the staged samples carry only the tile-relative rotation E; P_tile = exp(jw(g0 + B)) commutes
         // with the filter.  The discriminator output y[m] conj(y[m-1]) does not depend on it (|P| = 1), so with DISC
         // it is only applied to the two samples that cross the call boundary (prev_in / prev_out).
