@@ -331,12 +331,33 @@ def run_b200(args):
             err = float(np.max(np.abs(got - ref))) / scale
             worst = max(worst, err)
             bad += int(not (err <= 1e-5))
+        # gather at the sink: rank 0 collects the last W/2 outputs of every rank and the first W/2 of its
+        # right neighbour and compares each joined window -- W outputs STRADDLING a shard boundary -- with one continuous
+        # oracle run
+        gathered = 0
+        if world > 1:
+            half = W // 2
+            edge = torch.cat([y[:half], y[n_out_step - half:n_out_step]]).contiguous()
+            parts = [torch.empty_like(edge) for _ in range(world)] if rank == 0 else None
+            dist.gather(edge, parts, dst=0)
+            if rank == 0:
+                per = n // 25
+                for r in range(1, world):
+                    got = torch.cat([parts[r - 1][half:], parts[r][:half]]).cpu().numpy()
+                    ref = oracle_window(O, r * per - half, W)
+                    scale = max(1.0, float(np.max(np.abs(ref))))
+                    err = float(np.max(np.abs(got - ref))) / scale
+                    worst = max(worst, err)
+                    bad += int(not (err <= 1e-5))
+                    gathered += 1
         res = torch.tensor([worst, float(bad)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(res, op=dist.ReduceOp.MAX)
-        check = {"windows_per_rank": len(set(wins)), "window_outputs": W, "max_rel_err": float(res[0].item()), "ok": res[1].item() == 0.0,
-                 "what": "output windows at each rank's chunk start (straddling the shard boundary for rank > 0), middle and end vs "
-                         "the numpy oracle run cold %d samples before the window" % ORACLE_LEAD}
+        check = {"windows_per_rank": len(set(wins)), "window_outputs": W, "boundary_windows_gathered_at_rank0": gathered,
+                 "max_rel_err": float(res[0].item()), "ok": res[1].item() == 0.0,
+                 "what": "output windows at each rank's chunk start, middle and end vs the numpy oracle run cold %d samples before the "
+                         "window; plus, gathered at rank 0, one window straddling every shard boundary (last outputs of rank r-1 + "
+                         "first outputs of rank r) vs one continuous oracle run" % ORACLE_LEAD}
         if not check["ok"]:
             if rank == 0:
                 emit(json.dumps({"error": "parity check failed", "check": check}))

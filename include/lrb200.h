@@ -194,10 +194,15 @@ lrb200_block_t* lrb200_upsample_create(unsigned factor, unsigned elem_size, unsi
  * lrb200_pll_create replaces PLLBlock:process (radio/blocks/signal/pll.lua:113-170): loop constants from
  * (loop_bandwidth, frequency_min, frequency_max) in Hz at `rate`, output 0 = exp(j phi_multiplied) (ComplexFloat32),
  * output 1 = phase error (Float32); execute through lrb200_block_execute_multi with one input and two outputs.  The
- * recurrence is nonlinear and is run in stream order by one thread (exact, a few MS/s). */
+ * recurrence is nonlinear and is run in stream order by one thread (exact, a few MS/s).  lrb200_pll_set_mode(q, 1) opts
+ * into the chunk-parallel form for long calls: each chunk is simulated by its own thread after a lead-in of
+ * 24 / (zeta * loop bandwidth) samples from the phase of the input and the centre frequency, and the multiplied phase is
+ * rebuilt exactly from prefix sums of the per-chunk phase increments and errors -- equal to the sequential recurrence (to
+ * float32 resolution) WHILE THE LOOP IS LOCKED, not while it acquires or free-runs on noise. */
 lrb200_block_t* lrb200_binary_create(const char* op, unsigned complex_data, unsigned flags);
 lrb200_block_t* lrb200_pll_create(double loop_bandwidth, double frequency_min, double frequency_max, double multiplier,
                                   double rate, unsigned flags);
+int lrb200_pll_set_mode(lrb200_block_t* q, int mode);
 lrb200_block_t* lrb200_delay_create(unsigned num_samples, unsigned elem_size, unsigned flags);
 lrb200_block_t* lrb200_psd_create(unsigned num_samples, const float32_t* window, double scale, unsigned logarithmic,
                                   unsigned complex_data, unsigned flags);

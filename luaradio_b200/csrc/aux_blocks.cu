@@ -183,13 +183,113 @@ __global__ void pll_kernel(const float2* __restrict__ x, long long n, float2* __
     state[0] = phi; state[1] = phim; state[2] = freq;
 }
 
+// ---- chunk-parallel PLL (opt-in, lrb200_pll_set_mode(q, 1)).  Valid while the loop is LOCKED: from a phase guess
+// arg(x) and the centre frequency the second-order loop converges to the stream's own (phi_locked, freq_locked)
+// trajectory within W = 24 / (zeta * loop bandwidth) samples, so every chunk can be simulated by its own thread after a
+// W-sample lead-in (chunk 0 starts from the carried state and is exact).  phi_multiplied is NOT a function of the locked
+// state (it integrates multiplier * freq + alpha * error over the whole past), so it is rebuilt exactly from prefix sums
+// over the chunks: with A[i] = sum_{k<i} (freq'_k + alpha e_k) and E[i] = sum_{k<i} e_k,
+//     phi_multiplied[i] = phi_multiplied[0] + m A[i] + (1 - m) alpha E[i]     (mod 2 pi).
+struct PllChunk { double freq0, dA, dE, phi_end, freq_end, A0, E0; };
+
+__device__ __forceinline__ float pll_step(float2 xv, double& phi, double& freq, const PllParams& P, double& inc) {
+    const double two_pi = 6.283185307179586476925286766559;
+    double s, c;
+    sincos(phi, &s, &c);
+    const float vr = (float)c, vi = (float)s;
+    const float pr = (float)((double)xv.x * (double)vr - (double)xv.y * (double)(-vi));
+    const float pi = (float)((double)xv.x * (double)(-vi) + (double)xv.y * (double)vr);
+    const float e = atan2f(pi, pr);
+    freq = freq + P.beta * (double)e;
+    inc = freq + P.alpha * (double)e;
+    phi = phi + inc;
+    freq = freq > P.fmax ? P.fmax : freq;
+    freq = freq < P.fmin ? P.fmin : freq;
+    phi = phi > two_pi ? phi - two_pi : phi;
+    phi = phi < -two_pi ? phi + two_pi : phi;
+    return e;
+}
+
+__global__ void __launch_bounds__(128)
+pll_sim_kernel(const float2* __restrict__ x, long long n, float* __restrict__ err, long long L, long long W, int nchunks,
+               const double* __restrict__ state, PllParams P, PllChunk* __restrict__ chunks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const long long start = (long long)c * L, end = start + L < n ? start + L : n;
+    double phi, freq, inc;
+    if (c == 0) {
+        phi = state[0];
+        freq = state[2];
+    } else {
+        const long long begin = start - W;                       // L >= W, so begin >= 0
+        const float2 x0 = x[begin];
+        phi = (double)atan2f(x0.y, x0.x);
+        freq = 0.5 * (P.fmin + P.fmax);
+        for (long long i = begin; i < start; ++i) pll_step(x[i], phi, freq, P, inc);
+    }
+    PllChunk r;
+    r.freq0 = freq;
+    double dA = 0.0, dE = 0.0;
+    for (long long i = start; i < end; ++i) {
+        const float e = pll_step(x[i], phi, freq, P, inc);
+        err[i] = e;
+        dA += inc;
+        dE += (double)e;
+    }
+    r.dA = dA; r.dE = dE; r.phi_end = phi; r.freq_end = freq; r.A0 = 0.0; r.E0 = 0.0;
+    chunks[c] = r;
+}
+
+__global__ void pll_prefix_kernel(PllChunk* chunks, int nchunks, double* state, PllParams P) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const double two_pi = 6.283185307179586476925286766559;
+    double A = 0.0, E = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        chunks[c].A0 = A; chunks[c].E0 = E;
+        A += chunks[c].dA; E += chunks[c].dE;
+    }
+    // carried state for the next call; state[3] keeps this call's phi_multiplied[0] for the output kernel
+    state[3] = state[1];
+    state[0] = chunks[nchunks - 1].phi_end;
+    state[2] = chunks[nchunks - 1].freq_end;
+    state[1] = fmod(state[1] + P.mult * A + (1.0 - P.mult) * P.alpha * E, two_pi);
+}
+
+__global__ void __launch_bounds__(128)
+pll_out_kernel(const float* __restrict__ err, long long n, float2* __restrict__ out, long long L, int nchunks,
+               const double* __restrict__ state, PllParams P, const PllChunk* __restrict__ chunks) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const long long start = (long long)c * L, end = start + L < n ? start + L : n;
+    const double phim0 = state[3];
+    double A = chunks[c].A0, E = chunks[c].E0, freq = chunks[c].freq0;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (long long i = start; i < end; ++i) {
+        double ph = phim0 + P.mult * A + (1.0 - P.mult) * P.alpha * E;
+        ph -= two_pi * floor(ph / two_pi);                  // keep sincos in its accurate range
+        double s, cc;
+        sincos(ph, &s, &cc);
+        out[i] = make_float2((float)cc, (float)s);
+        const double e = (double)err[i];
+        freq = freq + P.beta * e;
+        A += freq + P.alpha * e;
+        E += e;
+        freq = freq > P.fmax ? P.fmax : freq;
+        freq = freq < P.fmin ? P.fmin : freq;
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 struct PllBlock : Block {
     PllParams P;
     double init_freq;
-    double* d_state = nullptr;
+    double* d_state = nullptr;      // phi_locked, phi_multiplied, freq_locked, (scratch) phi_multiplied at call start
+    int mode = 0;                   // 0 = exact sequential, 1 = chunk-parallel (locked loop)
+    long long warm = 0;             // lead-in of the chunk-parallel form
+    PllChunk* d_chunks = nullptr;
+    int chunk_cap = 0;
     PllBlock(double loop_bw_hz, double fmin_hz, double fmax_hz, double multiplier, double rate, bool dev) {
         name = "pll";
         in_size = 8;
@@ -207,8 +307,9 @@ struct PllBlock : Block {
         P.beta = (4 * bw * bw) / denom;
         P.mult = multiplier;
         init_freq = (P.fmin + P.fmax) / 2.0;
+        warm = (long long)std::ceil(24.0 / (damping * bw));
     }
-    ~PllBlock() override { cudaFree(d_state); }
+    ~PllBlock() override { cudaFree(d_state); cudaFree(d_chunks); }
     size_t out_size_of(int port) const override { return port == 0 ? 8 : 4; }
     long long memory_in() const override { return -1; }        // the multiplied phase integrates the whole past
     int set_state(cudaStream_t s) {
@@ -217,7 +318,7 @@ struct PllBlock : Block {
         return 0;
     }
     int init() override {
-        LRB_CHECK(cudaMalloc(&d_state, 3 * sizeof(double)));
+        LRB_CHECK(cudaMalloc(&d_state, 4 * sizeof(double)));
         if (set_state(ctx().stream) != 0) return -1;
         LRB_CHECK(cudaStreamSynchronize(ctx().stream));
         return 0;
@@ -231,6 +332,25 @@ struct PllBlock : Block {
         if (nin != 1 || nout != 2) { set_error("pll: expected 1 input and 2 outputs"); return -1; }
         *n_out = n;
         if (n == 0) return 0;
+        const long long L = warm * 4 > 16384 ? warm * 4 : 16384;
+        if (mode == 1 && (long long)n >= 2 * L) {
+            const int nchunks = (int)(((long long)n + L - 1) / L);
+            if (nchunks > chunk_cap) {
+                LRB_CHECK(cudaStreamSynchronize(s));
+                cudaFree(d_chunks);
+                d_chunks = nullptr;
+                LRB_CHECK(cudaMalloc(&d_chunks, sizeof(PllChunk) * (size_t)nchunks));
+                chunk_cap = nchunks;
+            }
+            const int blocks = (nchunks + 127) / 128;
+            pll_sim_kernel<<<blocks, 128, 0, s>>>((const float2*)dx[0], (long long)n, (float*)dy[1], L, warm, nchunks, d_state, P, d_chunks);
+            pll_prefix_kernel<<<1, 32, 0, s>>>(d_chunks, nchunks, d_state, P);
+            pll_out_kernel<<<blocks, 128, 0, s>>>((const float*)dy[1], (long long)n, (float2*)dy[0], L, nchunks, d_state, P, d_chunks);
+            count_launch(3);
+            LRB_CHECK(cudaGetLastError());
+            consumed += n;
+            return 0;
+        }
         pll_kernel<<<1, 32, 0, s>>>((const float2*)dx[0], (long long)n, (float2*)dy[0], (float*)dy[1], d_state, P);
         count_launch();
         LRB_CHECK(cudaGetLastError());
@@ -389,6 +509,14 @@ lrb200_block_t* lrb200_pll_create(double loop_bandwidth, double frequency_min, d
     if (!(rate > 0.0) || !(loop_bandwidth > 0.0) || !std::isfinite(multiplier)) { set_error("pll: rate and loop bandwidth must be positive"); return nullptr; }
     if (!(frequency_min <= frequency_max)) { set_error("pll: frequency_min must not exceed frequency_max"); return nullptr; }
     return wrap_aux(new (std::nothrow) PllBlock(loop_bandwidth, frequency_min, frequency_max, multiplier, rate, (flags & LRB200_DEVICE) != 0));
+}
+
+int lrb200_pll_set_mode(lrb200_block_t* q, int mode) {
+    PllBlock* p = q && q->impl ? dynamic_cast<PllBlock*>(q->impl) : nullptr;
+    if (!p) { set_error("not a PLL handle"); return -1; }
+    if (mode != 0 && mode != 1) { set_error("pll: mode must be 0 (exact, sequential) or 1 (chunk-parallel, locked loop)"); return -1; }
+    p->mode = mode;
+    return 0;
 }
 
 lrb200_block_t* lrb200_delay_create(unsigned num_samples, unsigned elem_size, unsigned flags) {

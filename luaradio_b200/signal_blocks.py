@@ -455,6 +455,8 @@ class PLLBlock(GPUMultiBlock):
     """pll.lua:27-170: in -> out (exp(j * multiplied phase)), error (phase detector output)."""
     name = "PLLBlock"
 
+    parallel = False          # True: chunk-parallel form for long vectors (valid while the loop is locked; lrb200_pll_set_mode)
+
     def instantiate(self, loop_bandwidth, frequency_min, frequency_max, multiplier=None):
         assert loop_bandwidth is not None, "Missing argument #1 (loop_bandwidth)"
         assert frequency_min is not None, "Missing argument #2 (frequency_min)"
@@ -464,5 +466,9 @@ class PLLBlock(GPUMultiBlock):
         self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32), Output("error", Float32)])
 
     def _make_handle(self, flags):
-        return _lib.check_handle(_lib.load().lrb200_pll_create(self.loop_bw, self.freq_min, self.freq_max, self.multiplier, self.get_rate(), flags),
-                                 "lrb200 pll object")
+        lib = _lib.load()
+        h = _lib.check_handle(lib.lrb200_pll_create(self.loop_bw, self.freq_min, self.freq_max, self.multiplier, self.get_rate(), flags),
+                              "lrb200 pll object")
+        if self.parallel:
+            _lib.check(lib.lrb200_pll_set_mode(h, 1), "pll_set_mode")
+        return h

@@ -343,3 +343,35 @@ def test_superchunk_scheduler_with_small_vectors():
     ref = O.wbfm_mono_chain().process(x)
     close(run(0), ref)
     close(run(1 << 17), ref)
+
+
+def test_pll_chunk_parallel_mode_when_locked():
+    """lrb200_pll_set_mode(1): every chunk simulated by its own thread after a lead-in, the multiplied phase rebuilt from
+    prefix sums.  Equal to the sequential recurrence while the loop is locked; the first chunk (carried state) is exact."""
+    rate, n = 220500.0, 700000
+    rng = np.random.default_rng(6)
+    t = np.arange(n) / rate
+    x = (0.8 * np.exp(2j * np.pi * 19000.3 * t + 0.4j) + 0.02 * rnd_c(rng, n)).astype(np.complex64)
+    ref = O.PLL(100, 19e3 - 50, 19e3 + 50, 2, rate)
+    ro, re_ = ref.process(x)
+    for multiplier, ref_out in ((2, ro), (0.25, None)):
+        blk = radio.PLLBlock(100, 19e3 - 50, 19e3 + 50, multiplier)
+        blk.parallel = True
+        blk.get_rate = lambda: rate
+        blk.differentiate([ComplexFloat32])
+        blk.initialize()
+        # first call: acquisition inside chunk 0 of a short (sequential) call, then two long chunk-parallel calls
+        cuts = [(0, 60000), (60000, 380000), (380000, n)]
+        outs, errs = [], []
+        for a, b in cuts:
+            o, e = blk.process(Vector.cast(x[a:b]))
+            outs.append(np.array(o.data, copy=True))
+            errs.append(np.array(e.data, copy=True))
+        got_o, got_e = np.concatenate(outs), np.concatenate(errs)
+        if ref_out is None:
+            ref_out, _ = O.PLL(100, 19e3 - 50, 19e3 + 50, multiplier, rate).process(x)
+        close(got_e[:60000], re_[:60000], absolute=2e-5)            # sequential part: as test_pll_matches_the_restatement
+        d_e = float(np.max(np.abs(got_e[60000:] - re_[60000:])))
+        d_o = float(np.max(np.abs(got_o[60000:] - ref_out[60000:])))
+        assert d_e <= 2e-4 and d_o <= 2e-4, (multiplier, d_e, d_o)
+        blk.cleanup()
