@@ -20,9 +20,9 @@ FM IQ at 1.1025 MS/s per GPU (weak scaling).  A "step" is one pass of the chain 
               samples (radio/core/pipe.lua:73, radio/blocks/sources/zero.lua:30), synchronous per call and in
               super-chunk mode (lrb200_graph_set_superchunk).
   N > 1     : the stream is sharded by time chunk.  Each step rank r sends the last HALO input samples of its chunk to
-              rank r+1 (NCCL P2P over NVLink, on its own stream) while every rank already runs its chunk from a cold
-              state; only a head piece of 2*HALO samples waits for the neighbour (lrb200_graph_execute_shard) and
-              replaces the chunk's first HALO/25 outputs.  HALO = lrb200_graph_halo().
+              rank r+1 (copy engine through a CUDA-IPC peer pointer, or NCCL P2P with --halo nccl; on its own stream) while
+              every rank already runs its stream cold from HALO samples early; only the first stage's few tiles that read
+              the neighbour's samples wait for them (lrb200_graph_execute_shard).  HALO = lrb200_graph_halo().
   check     : every rank re-computes windows of its output with the numpy oracle run cold from HALO samples before the
               window (the first window straddles the rank's left chunk boundary) and the run FAILS on a mismatch.
   --impl reference : the C restatement of the reference's CPU path (oracle/lr_oracle.c: VOLK dot-product FIRs and the
@@ -208,7 +208,7 @@ def run_b200(args):
     g = build_chain_graph(lib, _lib)
     HALO = int(lib.lrb200_graph_halo(g))
     assert HALO > 0 and HALO % 25 == 0, HALO
-    g_head = build_chain_graph(lib, _lib) if world > 1 else None
+    g_head = None
     # this rank's chunk lives at x[HALO:], the halo from the left neighbour is received into x[:HALO]
     xp = lib.lrb200_malloc((n + HALO) * 8)                 # a plain cudaMalloc allocation: exportable to the neighbour process
     assert xp, _lib.last_error()
@@ -263,7 +263,7 @@ def run_b200(args):
                     _lib.check(lib.lrb200_memcpy_d2d(ctypes.c_void_p(xp), ctypes.c_void_p(xt.data_ptr()), HALO * 8,
                                                      ctypes.c_void_p(comm.cuda_stream)), "unstage halo")
                 halo_ev.record(comm)
-            _lib.check(lib.lrb200_graph_execute_shard(g, g_head, ctypes.c_void_p(xp), HALO, n, start, ctypes.c_void_p(y.data_ptr()),
+            _lib.check(lib.lrb200_graph_execute_shard(g, None, ctypes.c_void_p(xp), HALO, n, start, ctypes.c_void_p(y.data_ptr()),
                                                       ctypes.byref(n_out), ctypes.c_void_p(halo_ev.cuda_event)), "execute_shard")
         else:
             _lib.check(lib.lrb200_graph_reset(g), "reset")
@@ -469,7 +469,7 @@ def run_b200(args):
             "config": {"workload": args.workload if total == WORKLOADS[args.workload] else "wbfm_mono_%d" % total,
                        "samples_per_gpu": n, "total_samples": world * n, "sample_rate_hz": RATE, "chain": CHAIN,
                        "graph": desc, "halo_samples": HALO if world > 1 else 0,
-                       "sharding": ("time-chunk; halo = %s on a side stream; head piece via lrb200_graph_execute_shard" %
+                       "sharding": ("time-chunk; halo = %s on a side stream; only the tiles that read it wait (lrb200_graph_execute_shard)" %
                                     {"ipc": "copy-engine read of the left neighbour's tail through a CUDA-IPC peer pointer over NVLink",
                                      "nccl": "NCCL P2P send/recv"}[transport]) if world > 1 else "single GPU",
                        "halo_transport": transport,

@@ -258,10 +258,11 @@ int    lrb200_graph_seek(lrb200_graph_t* g, uint64_t sample_index);
  * cold start needs before the outputs equal the streaming ones to float32 resolution (FIR histories, single-pole
  * decay to 1e-12, one discriminator sample), rounded up to 4 whole output periods (keeps buffers 16-byte aligned); < 0 if some stage has unbounded
  * memory.  lrb200_graph_execute_shard runs one chunk: dx -> DEVICE [halo samples of the left neighbour | n samples of
- * this chunk], the chunk starting at global input index `start`; the chunk's kernels start at once, only a head piece
- * of 2*halo samples (run by g_head, a second identical graph, on its own stream) waits for `halo_ready_event`
- * (a cudaEvent_t recorded after the neighbour's samples landed, or NULL), so the exchange overlaps the compute.
- * Asynchronous on the library stream; dy receives exactly the outputs of a single-device run for this chunk. */
+ * this chunk], the chunk starting at global input index `start`.  The stream is run cold from start - halo and the halo's
+ * outputs are dropped; only the first stage's few tiles that read the neighbour's samples wait for `halo_ready_event` (a
+ * cudaEvent_t recorded after those samples landed, or NULL if they are already there) on a side stream, everything else
+ * starts at once, so the exchange overlaps the chunk's kernels.  g_head is unused and may be NULL.  Asynchronous on the
+ * library stream; dy receives exactly the outputs of a single-device run for this chunk. */
 long long lrb200_graph_halo(lrb200_graph_t* g);
 int    lrb200_graph_execute_shard(lrb200_graph_t* g, lrb200_graph_t* g_head, const void* dx, size_t halo, size_t n,
                                   uint64_t start, void* dy, size_t* n_out, void* halo_ready_event);

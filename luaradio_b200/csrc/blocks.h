@@ -43,6 +43,13 @@ struct Block {
     virtual long long memory_in() const { return 0; }
     // output rate / input rate = up / down
     virtual void rate(unsigned* up, unsigned* down) const { *up = 1; *down = 1; }
+    // sharded runs: can this block's launch keep the launches that read the first Ctx::lead_samples inputs behind
+    // Ctx::lead_event while everything else starts at once?  (else the whole stream waits for the neighbour exchange)
+    virtual bool supports_lead_wait() const { return false; }
+    // is all carried state (history, previous output, pole state) read ONLY by launches this block puts on the side
+    // stream for a long call (edge tiles, history update)?  Then a short call may run entirely on the side stream and the
+    // next long call's interior kernel need not wait for it (run_shard's split of the last stage).
+    virtual bool state_only_on_side_stream() const { return false; }
     int execute(const void* x, size_t n, void* y, size_t* n_out);
     static int reserve(void** p, size_t* cap, size_t bytes);
 };
@@ -84,6 +91,8 @@ struct FirBlock : Block {
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
     long long memory_in() const override;
     void rate(unsigned* up, unsigned* down) const override { *up = 1; *down = (unsigned)D; }
+    bool supports_lead_wait() const override { return poly != nullptr && algo != 2 /* LRB200_FIR_FFT */ && !rotate; }
+    bool state_only_on_side_stream() const override { return poly != nullptr && algo != 2 && !rotate; }
     // fast paths (fir_fft.cu): fast_run returns 1 if it handled the call, 0 to fall back, <0 on error
     int fast_init();
     void fast_free();

@@ -20,6 +20,11 @@ struct Ctx {
     // persistent kernels leave this many CTA slots free while a sharded run has a head piece queued on another stream
     // (graph.cu: run_shard) -- otherwise the head's few small kernels only get an SM once the persistent grid drains
     int reserve_ctas = 0;
+    // time-chunk sharding: the first `lead_samples` input samples of the launch in flight come from the left neighbour and
+    // are only valid after `lead_event`; the polyphase launcher keeps every tile that touches them out of the interior
+    // kernel and makes its edge launch (side stream) wait for the event -- so only those few tiles wait for the exchange
+    long long lead_samples = 0;
+    cudaEvent_t lead_event = nullptr;
     // side stream for the few-CTA edge kernels, so they overlap the interior kernel instead of trailing it
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

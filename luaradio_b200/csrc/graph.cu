@@ -14,6 +14,7 @@
 #include "blocks.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -48,10 +49,8 @@ struct Graph {
     size_t sc_nout[2] = {0, 0};
     size_t sc_fill = 0, sc_outcap = 0;
     int sc_cur = 0;
-    // time-chunk sharding: output of the head piece (execute_shard) and the stream / events it runs on
+    // time-chunk sharding (run_shard): scratch for the outputs that belong to the halo
     void* head_out = nullptr; size_t head_out_cap = 0;
-    cudaStream_t s_head = nullptr;
-    cudaEvent_t ev_head = nullptr, ev_main = nullptr;
     // optional per-stage timing
     bool timing = false;
     std::vector<std::vector<cudaEvent_t>> tev;   // per stage: [start0, stop0, start1, stop1, ...]
@@ -78,9 +77,6 @@ struct Graph {
         if (s_d2h) cudaStreamDestroy(s_d2h);
         free_superchunk();
         cudaFree(head_out);
-        if (s_head) cudaStreamDestroy(s_head);
-        if (ev_head) cudaEventDestroy(ev_head);
-        if (ev_main) cudaEventDestroy(ev_main);
     }
 
     void free_superchunk() {
@@ -482,48 +478,95 @@ struct Graph {
     }
 
     // One time chunk of a sharded stream.  dx -> [halo samples of the left neighbour | n samples of this chunk], the chunk
-    // starting at global input index `start` (a multiple of the output period, like halo).  The chunk itself is run at
-    // once from a cold state on the compute stream; only a head piece of 2*halo samples -- run by `head` (a second,
-    // identical graph) on its own stream after `halo_ready` -- depends on the neighbour's data, and its last halo/period
-    // outputs replace the chunk's first (cold) ones.  So the neighbour exchange overlaps the chunk's kernels.
+    // starting at global input index `start` (a multiple of the output period, like halo).  The stream is run COLD from
+    // start - halo over halo + n samples -- every stage's memory has died out by `start` (halo()) -- and the halo's outputs
+    // are dropped.  Only what reads the neighbour's samples waits for `halo_ready`: the first stage keeps the few tiles
+    // that touch dx[0, halo) out of its interior kernel and runs them as edge tiles on the side stream behind the event
+    // (Ctx::lead_samples / lead_event); everything else starts at once, so the exchange overlaps the chunk's kernels.
+    // A first stage that cannot do that makes the compute stream wait for the event (the exchange is then serial).
+    // The last stage runs as two streaming calls -- the inputs that belong to the halo (their outputs go to a scratch
+    // buffer), then the rest straight into dy -- so dy receives exactly the chunk's outputs.  `head` is unused (kept in
+    // the C ABI for callers that built a second graph for the former head-piece scheme).
     int run_shard(Graph& head, const void* dx, size_t halo_n, size_t n, uint64_t start, void* dy, size_t* n_out, cudaEvent_t halo_ready) {
+        (void)head;
         if (!committed && commit(1) != 0) return -1;
+        if (stages.empty()) { set_error("graph: no blocks"); return -1; }
         cudaStream_t s = ctx().stream;
         const size_t isz = stages.front()->in_size, osz = stages.back()->out_size;
         unsigned long long up, down;
         total_rate(&up, &down);
         if (halo_n % down || start % down) { set_error("graph: halo and start must be multiples of %llu input samples", down); return -1; }
-        if (reset(s) != 0 || seek(start) != 0) return -1;
-        const bool has_head = halo_n != 0 && start != 0;
-        ctx().reserve_ctas = has_head ? 4 : 0;               // room for the head piece beside the persistent kernels
-        const int rc_main = run_device((const char*)dx + halo_n * isz, n, dy, n_out, s);
-        ctx().reserve_ctas = 0;
-        if (rc_main != 0) return -1;
-        if (!has_head) return 0;                             // the stream's first chunk: nothing to its left
-        if (start < halo_n || n < halo_n) { set_error("graph: chunk shorter than the halo"); return -1; }
-        if (!s_head) {
-            LRB_CHECK(cudaStreamCreateWithFlags(&s_head, cudaStreamNonBlocking));
-            LRB_CHECK(cudaEventCreateWithFlags(&ev_head, cudaEventDisableTiming));
-            LRB_CHECK(cudaEventCreateWithFlags(&ev_main, cudaEventDisableTiming));
+        if (halo_n == 0 || start == 0) {                     // the stream's first chunk: nothing to its left
+            if (reset(s) != 0 || seek(start) != 0) return -1;
+            return run_device((const char*)dx + halo_n * isz, n, dy, n_out, s);
         }
-        const size_t ho = (size_t)(halo_n / down * up);      // outputs per halo
-        const size_t cap = (head.max_output(2 * halo_n) + 1) * osz;
-        if (cap > head_out_cap) {
-            LRB_CHECK(cudaStreamSynchronize(s_head));
-            if (Block::reserve(&head_out, &head_out_cap, cap) != 0) return -1;
+        if (start < halo_n) { set_error("graph: chunk starts inside the halo"); return -1; }
+        if (reset(s) != 0 || seek(start - halo_n) != 0) return -1;
+        const size_t K = stages.size();
+        // inputs of every stage that belong to the halo: lead[k] = (stage-k input index of `start`) - (that of start - halo)
+        std::vector<size_t> lead(K + 1);
+        {
+            uint64_t a = start - halo_n, b = start;
+            for (size_t k = 0; k < K; ++k) {
+                lead[k] = (size_t)(b - a);
+                a = stages[k]->outputs_before(a);
+                b = stages[k]->outputs_before(b);
+            }
+            lead[K] = (size_t)(b - a);                       // outputs of the halo: dropped
         }
-        if (halo_ready) LRB_CHECK(cudaStreamWaitEvent(s_head, halo_ready, 0));
-        // the previous step's splice (on s) read head_out: do not overwrite it before that (ev_main was recorded right
-        // behind that splice; waiting on a never-recorded event is a no-op)
-        LRB_CHECK(cudaStreamWaitEvent(s_head, ev_main, 0));
-        size_t nh = 0;
-        if (head.reset(s_head) != 0 || head.seek(start - halo_n) != 0) return -1;
-        if (head.run_device(dx, 2 * halo_n, head_out, &nh, s_head) != 0) return -1;
-        if (nh != 2 * ho) { set_error("graph: head piece produced %zu outputs, expected %zu", nh, 2 * ho); return -1; }
-        LRB_CHECK(cudaEventRecord(ev_head, s_head));
-        LRB_CHECK(cudaStreamWaitEvent(s, ev_head, 0));
-        LRB_CHECK(cudaMemcpyAsync(dy, (const char*)head_out + ho * osz, ho * osz, cudaMemcpyDeviceToDevice, s));
-        LRB_CHECK(cudaEventRecord(ev_main, s));
+        const size_t ho = lead[K];
+        if ((ho + 1) * osz > head_out_cap) {
+            LRB_CHECK(cudaStreamSynchronize(s));
+            if (Block::reserve(&head_out, &head_out_cap, (ho + 1) * osz) != 0) return -1;
+        }
+        // ring for halo + n inputs
+        const size_t n_tot = halo_n + n;
+        size_t m = n_tot;
+        for (size_t k = 0; k + 1 < K; ++k) {
+            m = stages[k]->max_output(m);
+            const size_t bytes = (m ? m : 1) * stages[k]->out_size;
+            const int slot = (int)(k & 1);
+            if (bytes > ring_cap[slot]) {
+                LRB_CHECK(cudaStreamSynchronize(s));
+                if (Block::reserve(&ring[slot], &ring_cap[slot], bytes) != 0) return -1;
+            }
+        }
+        const bool overlap = halo_ready && K >= 2 && stages[0]->supports_lead_wait();
+        if (halo_ready && !overlap) LRB_CHECK(cudaStreamWaitEvent(s, halo_ready, 0));
+        const void* in = dx;
+        size_t cnt = n_tot;
+        int rc = 0;
+        for (size_t k = 0; k < K && rc == 0; ++k) {
+            const bool last = k + 1 == K;
+            if (timing) {
+                if (tcount.size() < K) { tev.resize(K); tcount.assign(K, 0); }
+                cudaEventRecord(timing_event(k, 2 * (size_t)tcount[k]), s);
+            }
+            if (k == 0 && overlap) { ctx().lead_samples = (long long)halo_n; ctx().lead_event = halo_ready; ctx().reserve_ctas = 4; }
+            size_t no = 0;
+            if (!last) {
+                void* out = ring[k & 1];
+                rc = stages[k]->run(in, cnt, out, &no, s);
+                in = out;
+                cnt = no;
+            } else {
+                // two streaming calls: the halo's share of the inputs -> scratch, the chunk's -> dy
+                // (the short first call goes to the side stream when the stage keeps every state access there: the second
+                // call's interior kernel then starts without waiting for the first call's latency-bound edge kernel)
+                size_t no1 = 0;
+                const size_t m1 = lead[k] < cnt ? lead[k] : cnt;
+                cudaStream_t s1 = (stages[k]->state_only_on_side_stream() && cnt - m1 >= SIDE_STREAM_MIN) ? side_fork(s) : s;
+                rc = stages[k]->run(in, m1, head_out, &no1, s1);
+                if (rc == 0 && no1 != ho) { set_error("graph: halo produced %zu outputs, expected %zu", no1, ho); rc = -1; }
+                if (rc == 0) rc = stages[k]->run((const char*)in + m1 * stages[k]->in_size, cnt - m1, dy, &no, s);
+                side_join(s, s1);
+                cnt = no;
+            }
+            if (k == 0) { ctx().lead_samples = 0; ctx().lead_event = nullptr; ctx().reserve_ctas = 0; }
+            if (timing) { cudaEventRecord(timing_event(k, 2 * (size_t)tcount[k] + 1), s); tcount[k]++; }
+        }
+        if (rc != 0) return -1;
+        *n_out = cnt;
         return 0;
     }
 
@@ -618,9 +661,9 @@ long long lrb200_graph_halo(lrb200_graph_t* g) {
 
 int lrb200_graph_execute_shard(lrb200_graph_t* g, lrb200_graph_t* g_head, const void* dx, size_t halo, size_t n,
                                uint64_t start, void* dy, size_t* n_out, void* halo_ready_event) {
-    if (!g || !g_head) { set_error("null graph"); return -1; }
+    if (!g) { set_error("null graph"); return -1; }
     size_t no = 0;
-    int rc = g->g.run_shard(g_head->g, dx, halo, n, start, dy, &no, (cudaEvent_t)halo_ready_event);
+    int rc = g->g.run_shard(g_head ? g_head->g : g->g, dx, halo, n, start, dy, &no, (cudaEvent_t)halo_ready_event);
     if (n_out) *n_out = no;
     return rc;
 }

@@ -480,11 +480,15 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
         P.hr[i] = (k >= 0 && k < Q * D) ? hr_base[k] : 0.0f;
     }
     const long long tiles = (n_out + TS - 1) / TS;
-    // interior tiles: every staged sample B(t) .. B(t)+LOADED-1 inside [0, n) and x 16-byte aligned
+    // interior tiles: every staged sample B(t) .. B(t)+LOADED-1 inside [lead, n) and x 16-byte aligned (lead > 0: the
+    // first samples arrive with the neighbour exchange of a sharded run, see Ctx::lead_samples)
+    cudaEvent_t lead_event = ctx().lead_samples > 0 ? ctx().lead_event : nullptr;
+    const long long lead = lead_event ? ctx().lead_samples : 0;
     long long t_lo = 0, t_hi = 0;
     if ((reinterpret_cast<uintptr_t>(x) & (REAL ? 7 : 15)) == 0) {
         const long long step = (long long)TS * D;
-        t_lo = off >= 0 ? 0 : (-off + step - 1) / step;
+        const long long need = lead - off;                                   // B(t) = off + t * step >= lead
+        t_lo = need <= 0 ? 0 : (need + step - 1) / step;
         const long long lim = n - (long long)S::LOADED - off - (REAL ? (long long)PAY * D : 0);
         t_hi = lim < 0 ? 0 : lim / step + 1;
         if (t_hi > tiles) t_hi = tiles;
@@ -492,8 +496,10 @@ int launch_shape(PolyParams P, const float* hr_base, const float2* x, const floa
     }
     const long long n_int = t_hi - t_lo, n_edge = tiles - n_int;
     // the edge tiles (first / last few) go to the side stream so that they overlap the interior kernel
-    cudaStream_t side = (n_int > 0 && n_edge > 0) ? side_fork(s) : s;
+    cudaStream_t side = ((n_int > 0 && n_edge > 0) || (lead_event && n_edge > 0)) ? side_fork(s) : s;
     if (n_edge > 0) {
+        if (lead_event && side != s) LRB_CHECK(cudaStreamWaitEvent(side, lead_event, 0));
+        else if (lead_event) LRB_CHECK(cudaStreamWaitEvent(s, lead_event, 0));
         kern_e<<<(unsigned)n_edge, PT_THREADS, S::SMEM, side>>>(x, hist, n, y, n_out, P, t_lo, t_hi, prev_in, prev_out, inv_gain);
         count_launch();
     }
@@ -672,6 +678,8 @@ struct TunerBlock : Block {
     size_t max_output(size_t n) const override { return n / D + 1; }
     uint64_t outputs_before(uint64_t idx) const override { return (idx + D - 1) / D; }
     long long memory_in() const override { return M - 1 + (disc ? D : 0); }
+    bool supports_lead_wait() const override { return true; }
+    bool state_only_on_side_stream() const override { return true; }
     void rate(unsigned* up, unsigned* down) const override { *up = 1; *down = (unsigned)D; }
     void reset_host() override { consumed = 0; cur = pcur = 0; }
     void state_buffers(std::vector<std::pair<void*, size_t>>& segs) override {
