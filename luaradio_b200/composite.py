@@ -467,7 +467,7 @@ class CompositeBlock(Block):
                     crawled[p] = resolve(self._connections[p])
         return crawled
 
-    def _prepare_to_run(self):
+    def _prepare_to_run(self, initialize=True):
         self._validate_inputs()
         self._differentiate()
         self._all_connections = self._crawl_connections()
@@ -487,18 +487,18 @@ class CompositeBlock(Block):
         for b in self._concrete_order:           # rate validation, composite.lua:394-414
             rates = [p.pipe.get_rate() for p in b.inputs]
             assert all(r == rates[0] for r in rates), 'Block "%s" input sample rate mismatch.' % b.name
-        for b in self._concrete_order:           # composite.lua:416-424: initialize every block
-            b.initialize()
+        if initialize:
+            for b in self._concrete_order:       # composite.lua:416-424: initialize every block
+                b.initialize()
 
     # ---------------------------------------------------------------------------------------------
     # GPU scheduler: maximal linear GPU runs -> GPUChainBlock, then round-robin over the reduced graph
     # ---------------------------------------------------------------------------------------------
-    def _collapse_gpu_runs(self, fuse, superchunk):
-        """Rewrite (self._all_connections, self._concrete_order): every maximal linear run of GPU blocks becomes one
-        GPUChainBlock (a run of one block keeps the block's own handle unless it borders a raw file source / sink); a raw
-        file source feeding only the run, and a raw file sink fed only by it, are absorbed as its first / last stage."""
-        orig = self._all_connections          # lookups use the untouched map; the rewrite goes into `conns`
-        conns = dict(orig)
+    def _plan_gpu_runs(self):
+        """Pure planning step (no device needed): every maximal linear run of GPU blocks in the flattened graph, as
+        [(blocks, absorbed raw file source or None, absorbed raw file sink or None)].  A run of ONE block is only kept
+        when it borders a raw file source / sink (otherwise the block's own handle does the same work)."""
+        orig = self._all_connections
         consumers = {}
         for inp, outp in orig.items():
             consumers.setdefault(outp, []).append(inp)
@@ -514,7 +514,7 @@ class CompositeBlock(Block):
             up = orig[b.inputs[0]].owner
             return up if is_gpu(up) and next_in_run(up) is b else None
 
-        chains = []
+        plan = []
         for b in list(self._concrete_order):
             if not is_gpu(b) or prev_in_run(b) is not None:
                 continue
@@ -528,6 +528,21 @@ class CompositeBlock(Block):
             snk = down[0].owner if len(down) == 1 and getattr(down[0].owner, "raw_sink", False) and len(down[0].owner.inputs) == 1 else None
             if len(run) < 2 and src is None and snk is None:
                 continue
+            plan.append((run, src, snk))
+        return plan
+
+    def _collapse_gpu_runs(self, fuse, superchunk):
+        """Rewrite (self._all_connections, self._concrete_order): every planned run becomes one GPUChainBlock; a raw file
+        source feeding only the run, and a raw file sink fed only by it, are absorbed as its first / last stage."""
+        orig = self._all_connections          # lookups use the untouched map; the rewrite goes into `conns`
+        conns = dict(orig)
+        consumers = {}
+        for inp, outp in orig.items():
+            consumers.setdefault(outp, []).append(inp)
+        chains = []
+        for run, src, snk in self._plan_gpu_runs():
+            up_port = orig[run[0].inputs[0]]
+            down = consumers.get(run[-1].outputs[0], [])
             chain = GPUChainBlock(run, src, snk, fuse, superchunk)
             chains.append(chain)
             for rb in run:

@@ -223,3 +223,59 @@ def test_public_header_is_plain_c(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     # on a box without a GPU the create call fails loudly with the library's own message and the program exits 0
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_scheduler_plans_maximal_gpu_runs_in_a_dag():
+    """CompositeBlock._plan_gpu_runs (the pure planning half of the GPU scheduler; its Lua twin is
+    lua/radio_b200/composite_patch.lua: collapse_gpu_runs): linear chain, fan-out, a two-input junction, a host block in the
+    middle, and the WBFM-stereo composite -- no device needed, nothing is initialised."""
+    import luaradio_b200 as radio
+    from luaradio_b200.block import Block, Input, Output
+    from luaradio_b200.types import ComplexFloat32
+
+    def plan(top):
+        top._prepare_to_run(initialize=False)
+        return [[b.name for b in run] for run, _, _ in top._plan_gpu_runs()]
+
+    x = np.zeros(16, np.complex64)
+    # 1. the mono chain: one run of all seven concrete blocks
+    top = radio.CompositeBlock()
+    top.connect(radio.ArraySource(x, 1102500.0), radio.TunerBlock(-250e3, 200e3, 5), radio.FrequencyDiscriminatorBlock(1.25),
+                radio.LowpassFilterBlock(128, 15e3), radio.FMDeemphasisFilterBlock(75e-6), radio.DownsamplerBlock(5), radio.ArraySink())
+    assert plan(top) == [["FrequencyTranslatorBlock", "LowpassFilterBlock", "DownsamplerBlock", "FrequencyDiscriminatorBlock",
+                          "LowpassFilterBlock", "FMDeemphasisFilterBlock", "DownsamplerBlock"]]
+
+    # 2. a host block splits the graph into two runs; a fan-out ends a run; single blocks stay on their own handle
+    class Host(Block):
+        name = "Host"
+
+        def instantiate(self):
+            self.add_type_signature([Input("in", ComplexFloat32)], [Output("out", ComplexFloat32)])
+
+    top = radio.CompositeBlock()
+    a1, a2, host, b1, b2, c1 = radio.FrequencyTranslatorBlock(1e5), radio.LowpassFilterBlock(64, 2e5), Host(), radio.DownsamplerBlock(2), \
+        radio.ComplexMagnitudeBlock(), radio.ComplexToRealBlock()
+    top.connect(radio.ArraySource(x, 1e6), a1, a2, host, b1)
+    top.connect(b1, b2, radio.ArraySink())
+    top.connect(b1, c1, radio.ArraySink())
+    assert plan(top) == [["FrequencyTranslatorBlock", "LowpassFilterBlock"]]
+
+    # 3. tests/top_spec.lua topology: two sources into a two-input block, then one run
+    top = radio.CompositeBlock()
+    mixer = radio.MultiplyConjugateBlock()
+    top.connect(radio.ArraySource(x, 1e6), "out", mixer, "in1")
+    top.connect(radio.ArraySource(x, 1e6), "out", mixer, "in2")
+    top.connect(mixer, radio.LowpassFilterBlock(16, 100e3), radio.FrequencyDiscriminatorBlock(5), radio.DecimatorBlock(25, {"num_taps": 16}),
+                radio.ArraySink())
+    assert plan(top) == [["LowpassFilterBlock", "FrequencyDiscriminatorBlock", "LowpassFilterBlock", "DownsamplerBlock"]]
+
+    # 4. WBFM stereo: discriminator -> hilbert, and the two lowpass -> complex-to-real arms
+    top = radio.CompositeBlock()
+    demod = radio.WBFMStereoDemodulator()
+    top.connect(radio.ArraySource(x, 220500.0), demod)
+    top.connect(demod, "left", radio.ArraySink(), "in")
+    top.connect(demod, "right", radio.ArraySink(), "in")
+    runs = plan(top)
+    assert ["FrequencyDiscriminatorBlock", "HilbertTransformBlock"] in runs
+    assert runs.count(["LowpassFilterBlock", "ComplexToRealBlock"]) == 2
+    assert all(len(r) >= 2 for r in runs)
