@@ -109,7 +109,15 @@ return function (radio)
     end
     radio.IQFileSink.process = sink_process(lib.lrb200_iqsink_create, "iqsink")
     radio.RealFileSink.process = sink_process(lib.lrb200_realsink_create, "realsink")
-    -- format_name: the constructor keeps the format string next to self.format (one added line in each instantiate()).
+    -- format_name: the reference's instantiate() keeps only the format TABLE (sources/iqfile.lua:48); the library wants the
+    -- format's name, so each constructor is wrapped to remember it (second argument in all four signatures)
+    for _, class in ipairs({radio.IQFileSource, radio.RealFileSource, radio.IQFileSink, radio.RealFileSink}) do
+        local instantiate = class.instantiate
+        class.instantiate = function (self, file, format, ...)
+            self.format_name = format
+            return instantiate(self, file, format, ...)
+        end
+    end
 
     -- the scheduler: connected GPU blocks share one device-resident flow graph (composite_patch.lua)
     require('radio_b200.composite_patch').install(radio)

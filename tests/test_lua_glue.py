@@ -104,3 +104,41 @@ def test_lua_block_structure_balances():
         text = strip_lua(open(os.path.join(LUA, f)).read())
         for a, b in ("()", "{}", "[]"):
             assert text.count(a) == text.count(b), "%s: unbalanced %s%s" % (f, a, b)
+
+
+# (reference file, field or method the glue relies on) -- verified against the reference tree when it is present (the build
+# container); on the GPU box /root/reference does not exist and the test is skipped
+GLUE_RELIES_ON = [
+    ("radio/blocks/signal/frequencytranslator.lua", "self.offset"), ("radio/blocks/signal/frequencydiscriminator.lua", "self.gain"),
+    ("radio/blocks/signal/downsampler.lua", "self.factor"), ("radio/blocks/signal/iirfilter.lua", "self.b_taps"),
+    ("radio/blocks/signal/iirfilter.lua", "self.a_taps"), ("radio/blocks/signal/hilberttransform.lua", "self.hilbert_taps"),
+    ("radio/blocks/signal/multiplyconstant.lua", "self.constant"), ("radio/blocks/signal/upsampler.lua", "self.factor"),
+    ("radio/blocks/signal/firfilter.lua", "self.taps"), ("radio/blocks/signal/firfilter.lua", "self.use_fft"),
+    ("radio/blocks/signal/firfilter.lua", "process_fft_complex_input_real_taps"), ("radio/blocks/signal/iirfilter.lua", "process_complex"),
+    ("radio/blocks/signal/multiplyconstant.lua", "process_complex_by_real"),
+    ("radio/blocks/sources/iqfile.lua", "self.raw_samples"), ("radio/blocks/sources/iqfile.lua", "self.repeat_on_eof"),
+    ("radio/blocks/sources/iqfile.lua", "self.file"), ("radio/blocks/sources/realfile.lua", "self.raw_samples"),
+    ("radio/blocks/sinks/iqfile.lua", "self.raw_samples"), ("radio/blocks/sinks/realfile.lua", "self.raw_samples"),
+    ("radio/blocks/sinks/wavfile.lua", "self.count"),
+    ("radio/core/composite.lua", "function CompositeBlock:_crawl_connections"), ("radio/core/composite.lua", "function CompositeBlock:start"),
+    ("radio/core/composite.lua", "function CompositeBlock:_connect_pipes"), ("radio/core/block.lua", "function Block:differentiate"),
+    ("radio/core/platform.lua", "platform.load"), ("radio/core/pipe.lua", "function Pipe:write"),
+]
+
+
+def test_fields_and_hooks_the_glue_relies_on_exist_in_the_reference():
+    import pytest
+    ref = os.environ.get("LUARADIO_REFERENCE", "/root/reference")
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this machine")
+    missing = []
+    for rel, needle in GLUE_RELIES_ON:
+        text = open(os.path.join(ref, rel)).read()
+        if needle not in text:
+            missing.append((rel, needle))
+    assert not missing, missing
+    # every class the glue patches is registered by the reference (radio/blocks/init.lua, radio/composites/init.lua)
+    reg = open(os.path.join(ref, "radio/blocks/init.lua")).read()
+    glue = open(os.path.join(LUA, "blocks_patch.lua")).read() + open(os.path.join(LUA, "firfilter_patch.lua")).read()
+    for cls in set(re.findall(r"radio\.(\w+Block|\w+Source|\w+Sink)\b", glue)):
+        assert re.search(r"\b%s\b" % cls, reg), "%s is not a reference block" % cls
