@@ -9,7 +9,7 @@
 // (M/D complex-by-real MACs per input sample) and the input is read from HBM exactly once:
 // algorithmic traffic 8 + 8/D bytes per input sample (8 + 4/D with the discriminator fused).
 //
-// Tile.  A CTA produces PT_TO = 128 threads x R = 8 consecutive decimated outputs from one shared-memory tile of
+// Tile.  A CTA produces PT_TO = PT_THREADS (64) threads x R = 8 consecutive decimated outputs from one shared-memory tile of
 // rotated input samples kept in their natural (interleaved) order.  With reversed taps hr[0 .. T), T = Q*D + 1
 // (Q = ceil(M/D); one spare leading tap lets the host make every tile start on an even input index, so every
 // global load is an aligned 128-bit load and there is a single code path), and B the first input the tile needs,
