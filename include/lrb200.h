@@ -275,6 +275,26 @@ int    lrb200_graph_set_timing(lrb200_graph_t* g, int enable);
 double lrb200_graph_stage_time_ms(lrb200_graph_t* g, int stage, int* executions);
 void   lrb200_graph_destroy(lrb200_graph_t* g);
 
+/* ---- device DAG: fan-out / fan-in between GPU nodes without host hops ------------------------------------------------
+ * Replaces, for a connected set of GPU blocks that is not a straight line, the same fork-per-block + socketpair plumbing
+ * (radio/core/composite.lua:568-636): composites/wbfmstereodemodulator.lua:22-64 and amsynchronousdemodulator.lua:25-45 run
+ * with every edge in device memory.  A node is a block created with LRB200_DEVICE (any number of ports) or a linear
+ * lrb200_graph_t (its fused kernels keep doing the work inside the run); nodes are added in topological order and are
+ * owned by the DAG afterwards.  An input / output reference is  node_id * 4 + output_port,  or -1 for the DAG's single
+ * input.  All inputs of a node must deliver the same number of samples per call (converging paths with equal rate
+ * changes; the reference's PipeMux, radio/core/pipe.lua:495-615, would buffer a surplus).  lrb200_dag_execute: HOST in,
+ * HOST outs -- one upload, the node launches in order, one download per output, one synchronize. */
+typedef struct lrb200_dag_s lrb200_dag_t;
+lrb200_dag_t* lrb200_dag_create(void);
+int    lrb200_dag_add_block(lrb200_dag_t* d, lrb200_block_t* q, const int* inputs, unsigned num_inputs);   /* node id or -1 */
+int    lrb200_dag_add_graph(lrb200_dag_t* d, lrb200_graph_t* g, int input);                                /* node id or -1 */
+int    lrb200_dag_set_outputs(lrb200_dag_t* d, const int* outputs, unsigned num_outputs);
+int    lrb200_dag_execute(lrb200_dag_t* d, const void* x, size_t n, void* const* y, size_t* n_out);        /* n_out[k] per output */
+size_t lrb200_dag_max_output(const lrb200_dag_t* d, unsigned output, size_t n);
+int    lrb200_dag_reset(lrb200_dag_t* d);
+const char* lrb200_dag_describe(const lrb200_dag_t* d);
+void   lrb200_dag_destroy(lrb200_dag_t* d);
+
 /* ---- synthetic sources on the device (the reference analogues are
  * radio/blocks/sources/{uniformrandom,signal}.lua) -- counter-based, so any window of the stream
  * can be regenerated on any GPU.  dst is a DEVICE pointer; async on the library stream. */

@@ -95,6 +95,15 @@ _PROTOS = {
     "lrb200_graph_set_timing": (c_int, [c_void_p, c_int]),
     "lrb200_graph_stage_time_ms": (c_double, [c_void_p, c_int, POINTER(c_int)]),
     "lrb200_graph_destroy": (None, [c_void_p]),
+    "lrb200_dag_create": (c_void_p, []),
+    "lrb200_dag_add_block": (c_int, [c_void_p, c_void_p, POINTER(c_int), c_uint]),
+    "lrb200_dag_add_graph": (c_int, [c_void_p, c_void_p, c_int]),
+    "lrb200_dag_set_outputs": (c_int, [c_void_p, POINTER(c_int), c_uint]),
+    "lrb200_dag_execute": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_void_p), POINTER(c_size_t)]),
+    "lrb200_dag_max_output": (c_size_t, [c_void_p, c_uint, c_size_t]),
+    "lrb200_dag_reset": (c_int, [c_void_p]),
+    "lrb200_dag_describe": (c_char_p, [c_void_p]),
+    "lrb200_dag_destroy": (None, [c_void_p]),
     "lrb200_synth_white_iq": (c_int, [c_void_p, c_uint64, c_size_t, c_uint32]),
     "lrb200_synth_fm_iq": (c_int, [c_void_p, c_uint64, c_size_t, c_uint32, c_double, c_double, c_double, c_float, c_float]),
 }

@@ -494,17 +494,61 @@ class CompositeBlock(Block):
     # ---------------------------------------------------------------------------------------------
     # GPU scheduler: maximal linear GPU runs -> GPUChainBlock, then round-robin over the reduced graph
     # ---------------------------------------------------------------------------------------------
-    def _plan_gpu_runs(self):
+    def _plan_gpu_dags(self):
+        """Pure planning step: connected sets of GPU blocks that are NOT a straight line (they contain a multi-port block
+        or an internal fan-out), fed by exactly one external output port -- candidates for ONE device DAG (lrb200_dag_*),
+        every edge in device memory.  Returns [(members in evaluation order, external producer port, [member output ports
+        read from outside])]."""
+        orig = self._all_connections
+        gpu = [b for b in self._concrete_order if isinstance(b, GPUBlock) and b.inputs and b.outputs]
+        gset = set(gpu)
+        adj = {b: set() for b in gpu}
+        for inp, outp in orig.items():
+            if inp.owner in gset and outp.owner in gset:
+                adj[inp.owner].add(outp.owner)
+                adj[outp.owner].add(inp.owner)
+        seen, plans = set(), []
+        for b in gpu:
+            if b in seen:
+                continue
+            comp, todo = set(), [b]
+            while todo:
+                c = todo.pop()
+                if c in comp:
+                    continue
+                comp.add(c)
+                todo.extend(adj[c] - comp)
+            seen |= comp
+            members = [m for m in self._concrete_order if m in comp]
+            fan_out = any(sum(1 for i, o in orig.items() if o is p and i.owner in comp) > 1 for m in members for p in m.outputs)
+            if len(members) < 2 or not (fan_out or any(len(m.inputs) > 1 or len(m.outputs) > 1 for m in members)):
+                continue                                     # a straight line: the chain planner's business
+            ext_in = {orig[p] for m in members for p in m.inputs if orig[p].owner not in comp}
+            if len(ext_in) != 1:
+                continue                                     # several external feeds: stays a host-level graph
+            ext_out = []
+            for m in members:
+                for p in m.outputs:
+                    if any(o is p and i.owner not in comp for i, o in orig.items()):
+                        ext_out.append(p)
+            if not ext_out:
+                continue
+            plans.append((members, next(iter(ext_in)), ext_out))
+        return plans
+
+    def _plan_gpu_runs(self, exclude=()):
         """Pure planning step (no device needed): every maximal linear run of GPU blocks in the flattened graph, as
         [(blocks, absorbed raw file source or None, absorbed raw file sink or None)].  A run of ONE block is only kept
-        when it borders a raw file source / sink (otherwise the block's own handle does the same work)."""
+        when it borders a raw file source / sink (otherwise the block's own handle does the same work).  Blocks in
+        `exclude` (members of a device DAG) are not considered."""
         orig = self._all_connections
         consumers = {}
         for inp, outp in orig.items():
             consumers.setdefault(outp, []).append(inp)
+        exclude = set(exclude)
 
         def is_gpu(b):
-            return isinstance(b, GPUBlock) and len(b.inputs) == 1 and len(b.outputs) == 1
+            return isinstance(b, GPUBlock) and len(b.inputs) == 1 and len(b.outputs) == 1 and b not in exclude
 
         def next_in_run(b):
             c = consumers.get(b.outputs[0], [])
@@ -531,16 +575,30 @@ class CompositeBlock(Block):
             plan.append((run, src, snk))
         return plan
 
-    def _collapse_gpu_runs(self, fuse, superchunk):
-        """Rewrite (self._all_connections, self._concrete_order): every planned run becomes one GPUChainBlock; a raw file
-        source feeding only the run, and a raw file sink fed only by it, are absorbed as its first / last stage."""
+    def _collapse_gpu_runs(self, fuse, superchunk, device_dag=True):
+        """Rewrite (self._all_connections, self._concrete_order): every planned device DAG becomes one GPUDagBlock, every
+        planned run one GPUChainBlock; a raw file source feeding only a run, and a raw file sink fed only by it, are absorbed
+        as its first / last stage."""
         orig = self._all_connections          # lookups use the untouched map; the rewrite goes into `conns`
         conns = dict(orig)
         consumers = {}
         for inp, outp in orig.items():
             consumers.setdefault(outp, []).append(inp)
-        chains = []
-        for run, src, snk in self._plan_gpu_runs():
+        chains, dag_members = [], set()
+        for members, ext_in, ext_out in (self._plan_gpu_dags() if device_dag else []):
+            dag = GPUDagBlock(members, ext_in, ext_out, orig, fuse)
+            chains.append(dag)
+            dag_members.update(members)
+            for m in members:
+                for p in m.inputs:
+                    del conns[p]
+            conns[dag.inputs[0]] = ext_in
+            dag.inputs[0].pipe = next(p for m in members for p in m.inputs if orig[p] is ext_in).pipe
+            for k, port in enumerate(ext_out):
+                for cin in consumers.get(port, []):
+                    if cin.owner not in dag_members:
+                        conns[cin] = dag.outputs[k]
+        for run, src, snk in self._plan_gpu_runs(dag_members):
             up_port = orig[run[0].inputs[0]]
             down = consumers.get(run[-1].outputs[0], [])
             chain = GPUChainBlock(run, src, snk, fuse, superchunk)
@@ -558,7 +616,7 @@ class CompositeBlock(Block):
         absorbed = set()
         for c in chains:
             absorbed.update(c.blocks)
-            absorbed.update(x for x in (c.raw_source, c.raw_sink) if x is not None)
+            absorbed.update(x for x in (getattr(c, "raw_source", None), getattr(c, "raw_sink", None)) if x is not None)
         blocks = [b for b in self._concrete_order if b not in absorbed] + chains
         self._chains = chains
         self._run_connections = conns
@@ -624,9 +682,9 @@ class CompositeBlock(Block):
                     if r is not None:
                         push(b, (r,))
 
-    def _run_body(self, fuse, superchunk):
+    def _run_body(self, fuse, superchunk, device_dag=True):
         try:
-            self._collapse_gpu_runs(fuse, superchunk)
+            self._collapse_gpu_runs(fuse, superchunk, device_dag)
             self._schedule()
         finally:
             # composite.lua:693-696: clean up every block, whatever happened (native handles, file sinks, WAV header)
@@ -641,7 +699,7 @@ class CompositeBlock(Block):
                 raise first
 
     # -- composite.lua:534-545 start, :858 status, :886 stop, :913 wait, :937 run
-    def start(self, multiprocess=False, fuse=True, superchunk=0):
+    def start(self, multiprocess=False, fuse=True, superchunk=0, device_dag=True):
         """Prepare the flow graph and start running it on a scheduler thread.  `multiprocess` is accepted for API
         compatibility; the GPU scheduler is always single-process (a CUDA context does not survive fork())."""
         if getattr(self, "_running", False):
@@ -655,7 +713,7 @@ class CompositeBlock(Block):
             try:
                 if device >= 0:
                     _lib.check(lib.lrb200_init(device), "lrb200_init")      # the CUDA device is a per-thread setting
-                self._run_body(fuse, superchunk)
+                self._run_body(fuse, superchunk, device_dag)
             except BaseException as e:      # surfaced by wait()
                 self._error = e
             finally:
@@ -688,15 +746,16 @@ class CompositeBlock(Block):
             err, self._error = self._error, None
             raise err
 
-    def run(self, multiprocess=False, fuse=True, superchunk=0):
-        """start() + wait() (composite.lua:937-941), on the calling thread."""
+    def run(self, multiprocess=False, fuse=True, superchunk=0, device_dag=True):
+        """start() + wait() (composite.lua:937-941), on the calling thread.  device_dag=False keeps non-linear GPU parts as
+        host-level graphs of chains and single blocks (a host round trip at every junction)."""
         if getattr(self, "_running", False):
             raise RuntimeError("CompositeBlock already running!")
         self._prepare_to_run()
         self._stop_requested, self._error = False, None
         self._running = True
         try:
-            self._run_body(fuse, superchunk)
+            self._run_body(fuse, superchunk, device_dag)
         finally:
             self._running = False
         return self
@@ -777,6 +836,92 @@ class GPUChainBlock(Block):
         if self.graph:
             self._lib.lrb200_graph_destroy(self.graph)
             self.graph = None
+
+
+class GPUDagBlock(Block):
+    """A connected, non-linear set of GPU blocks as ONE device DAG (lrb200_dag_*): every edge between them is a device
+    buffer; the only host traffic is the set's single input and its outputs.  Linear runs inside the set are added as fused
+    lrb200 flow graphs, the rest (two-input blocks, PLL, lone blocks) as single nodes."""
+    name = "GPUDagBlock"
+
+    def instantiate(self, members, ext_in, ext_out, connections, fuse=True):
+        self.blocks, self.ext_in, self.ext_out, self.fuse = list(members), ext_in, list(ext_out), fuse
+        self._conn = connections
+        self.dag, self.desc = None, ""
+        self.add_type_signature([Input("in", ext_in.data_type)], [Output("out%d" % (k + 1), p.data_type) for k, p in enumerate(ext_out)])
+        self.differentiate([ext_in.data_type])
+
+    def get_rate(self):
+        return self.ext_out[0].owner.get_rate()
+
+    def initialize(self):
+        lib = self._lib = _lib.require_device()
+        d = self.dag = _lib.check_handle(lib.lrb200_dag_create(), "lrb200 dag")
+        conn, members = self._conn, set(self.blocks)
+        consumers = {}
+        for inp, outp in conn.items():
+            consumers.setdefault(outp, []).append(inp)
+        ref = {self.ext_in: -1}                      # output port -> DAG reference
+
+        def simple(b):
+            return len(b.inputs) == 1 and len(b.outputs) == 1
+
+        def next_in_run(b):                          # the single member consumer of a simple block, if that edge is 1:1
+            c = consumers.get(b.outputs[0], [])
+            return c[0].owner if len(c) == 1 and c[0].owner in members and simple(c[0].owner) else None
+
+        done = set()
+        for b in self.blocks:                        # evaluation order == topological order
+            if b in done:
+                continue
+            if simple(b):
+                run, nb = [b], next_in_run(b)
+                while nb is not None and nb not in done:
+                    run.append(nb)
+                    nb = next_in_run(nb)
+                if len(run) >= 2:
+                    g = _lib.check_handle(lib.lrb200_graph_create(), "lrb200 graph")
+                    for rb in run:
+                        _lib.check(lib.lrb200_graph_append(g, rb.make_device_handle()), "graph_append(%s)" % rb.name)
+                    _lib.check(lib.lrb200_graph_commit(g, 1 if self.fuse else 0), "graph_commit")
+                    node = lib.lrb200_dag_add_graph(d, g, ref[conn[run[0].inputs[0]]])
+                    if node < 0:
+                        lib.lrb200_graph_destroy(g)
+                        raise _lib.LibraryError("dag_add_graph: " + _lib.last_error())
+                    ref[run[-1].outputs[0]] = node * 4
+                    done.update(run)
+                    continue
+            ins = (ctypes.c_int * len(b.inputs))(*[ref[conn[p]] for p in b.inputs])
+            h = b.make_device_handle()
+            node = lib.lrb200_dag_add_block(d, h, ins, len(b.inputs))
+            if node < 0:
+                lib.lrb200_block_destroy(h)
+                raise _lib.LibraryError("dag_add_block(%s): %s" % (b.name, _lib.last_error()))
+            for k, p in enumerate(b.outputs):
+                ref[p] = node * 4 + k
+            done.add(b)
+        outs = (ctypes.c_int * len(self.ext_out))(*[ref[p] for p in self.ext_out])
+        _lib.check(lib.lrb200_dag_set_outputs(d, outs, len(self.ext_out)), "dag_set_outputs")
+        self.desc = "dag{" + lib.lrb200_dag_describe(d).decode() + "}"
+        self.outs = [p.data_type.vector() for p in self.ext_out]
+        self._n_out = (ctypes.c_size_t * len(self.ext_out))()
+
+    def process(self, x):
+        lib, d = self._lib, self.dag
+        for k, o in enumerate(self.outs):
+            o.resize(lib.lrb200_dag_max_output(d, k, x.length))
+        ptrs = (ctypes.c_void_p * len(self.outs))(*[o.ctypes_ptr() for o in self.outs])
+        _lib.check(lib.lrb200_dag_execute(d, x.ctypes_ptr(), x.length, ptrs, self._n_out), "dag_execute")
+        res = tuple(o.resize(self._n_out[k]) for k, o in enumerate(self.outs))
+        return res[0] if len(res) == 1 else res
+
+    def flush(self):
+        return None
+
+    def cleanup(self):
+        if self.dag:
+            self._lib.lrb200_dag_destroy(self.dag)
+            self.dag = None
 
 
 # -------------------------------------------------------------------------------------------------

@@ -580,11 +580,138 @@ struct Graph {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Device DAG: fan-out / fan-in between GPU nodes without host hops.  A node is a multi-port block (MultiplyConjugate, Add,
+// Subtract, PLL, ...), a single block, or a committed LINEAR flow graph (so the fused kernels keep doing the work inside
+// every linear run).  Nodes are added in topological order; an input reference is (producer node, output port) or the
+// DAG's own input.  Every edge is a grow-only device buffer; all inputs of a node must deliver the same number of samples
+// per call (true whenever the converging paths have the same rate changes -- every block here is zero-latency; the
+// reference's PipeMux would buffer a surplus instead, radio/core/pipe.lua:495-615).  Host in, host out(s): one upload,
+// the node launches in order on the library stream, one download per output, one synchronize.
+// This is what composites/wbfmstereodemodulator.lua:22-64 and amsynchronousdemodulator.lua:25-45 need on the device.
+// ---------------------------------------------------------------------------------------------------------------------
+void destroy_graph_handle(void* holder);      // delete (lrb200_graph_t*) -- defined behind the handle type below
+
+struct DagNode {
+    Block* blk = nullptr;          // owned
+    Graph* sub = nullptr;          // a committed linear run: lives inside `holder` (the caller's former handle, owned)
+    void* holder = nullptr;
+    std::vector<int> in_refs;      // producer node * 4 + port, or -1 for the DAG input
+    std::vector<void*> out_buf;
+    std::vector<size_t> out_cap, out_cnt;
+    int nout() const { return sub ? 1 : blk->num_outputs; }
+    size_t out_size(int port) const { return sub ? sub->stages.back()->out_size : blk->out_size_of(port); }
+    size_t in_size() const { return sub ? sub->stages.front()->in_size : blk->in_size; }
+    const char* name() const { return sub ? sub->desc.c_str() : blk->name; }
+};
+
+struct Dag {
+    std::vector<DagNode> nodes;
+    std::vector<int> outputs;
+    void* d_in = nullptr; size_t d_in_cap = 0;
+    size_t in_size = 0;
+    std::string desc;
+
+    ~Dag() {
+        for (DagNode& nd : nodes) {
+            delete nd.blk;
+            if (nd.holder) destroy_graph_handle(nd.holder);
+            for (void* p : nd.out_buf) cudaFree(p);
+        }
+        cudaFree(d_in);
+    }
+
+    int add(Block* blk, Graph* sub, void* holder, const int* refs, unsigned nin) {
+        DagNode nd;
+        nd.blk = blk; nd.sub = sub; nd.holder = holder;
+        const int want = sub ? 1 : blk->num_inputs;
+        if ((int)nin != want) { set_error("dag: %s takes %d input(s), got %u", nd.name(), want, nin); return -1; }
+        for (unsigned i = 0; i < nin; ++i) {
+            const int r = refs[i];
+            size_t esz;
+            if (r == -1) {
+                if (in_size && in_size != nd.in_size()) { set_error("dag: the input feeds nodes of different sample sizes"); return -1; }
+                in_size = nd.in_size();
+                esz = in_size;
+            } else {
+                const int pn = r >> 2, pp = r & 3;
+                if (r < 0 || pn >= (int)nodes.size() || pp >= nodes[(size_t)pn].nout()) { set_error("dag: bad input reference %d", r); return -1; }
+                esz = nodes[(size_t)pn].out_size(pp);
+            }
+            if (esz != nd.in_size()) { set_error("dag: %zu-byte samples cannot feed %s (%zu-byte input)", esz, nd.name(), nd.in_size()); return -1; }
+            nd.in_refs.push_back(r);
+        }
+        nd.out_buf.assign((size_t)nd.nout(), nullptr);
+        nd.out_cap.assign((size_t)nd.nout(), 0);
+        nd.out_cnt.assign((size_t)nd.nout(), 0);
+        nodes.push_back(nd);
+        if (!desc.empty()) desc += " ; ";
+        desc += nd.name();
+        return (int)nodes.size() - 1;
+    }
+
+    int reset() {
+        for (DagNode& nd : nodes) {
+            if (nd.sub) { if (nd.sub->reset() != 0) return -1; }
+            else if (nd.blk->reset() != 0) return -1;
+        }
+        return 0;
+    }
+
+    int run_host(const void* x, size_t n, void* const* y, size_t* n_out) {
+        if (nodes.empty() || outputs.empty()) { set_error("dag: no nodes / no outputs"); return -1; }
+        cudaStream_t s = ctx().stream;
+        if (n * in_size > d_in_cap) {
+            LRB_CHECK(cudaStreamSynchronize(s));
+            if (Block::reserve(&d_in, &d_in_cap, n * in_size) != 0) return -1;
+        }
+        if (n) LRB_CHECK(cudaMemcpyAsync(d_in, x, n * in_size, cudaMemcpyHostToDevice, s));
+        for (DagNode& nd : nodes) {
+            std::vector<const void*> ins;
+            size_t cnt = 0;
+            for (size_t i = 0; i < nd.in_refs.size(); ++i) {
+                const int r = nd.in_refs[i];
+                const void* p = r == -1 ? d_in : nodes[(size_t)(r >> 2)].out_buf[(size_t)(r & 3)];
+                const size_t c = r == -1 ? n : nodes[(size_t)(r >> 2)].out_cnt[(size_t)(r & 3)];
+                if (i && c != cnt) { set_error("dag: %s received inputs of different lengths (%zu, %zu)", nd.name(), cnt, c); return -1; }
+                cnt = c;
+                ins.push_back(p);
+            }
+            const size_t mo = nd.sub ? nd.sub->max_output(cnt) : nd.blk->max_output(cnt);
+            for (int o = 0; o < nd.nout(); ++o) {
+                const size_t bytes = (mo ? mo : 1) * nd.out_size(o);
+                if (bytes > nd.out_cap[(size_t)o]) {
+                    LRB_CHECK(cudaStreamSynchronize(s));
+                    if (Block::reserve(&nd.out_buf[(size_t)o], &nd.out_cap[(size_t)o], bytes) != 0) return -1;
+                }
+            }
+            size_t no = 0;
+            if (nd.sub) {
+                if (nd.sub->run_device(ins[0], cnt, nd.out_buf[0], &no, s) != 0) return -1;
+            } else {
+                if (nd.blk->run_multi(ins.data(), (int)ins.size(), cnt, nd.out_buf.data(), nd.nout(), &no, s) != 0) return -1;
+            }
+            for (int o = 0; o < nd.nout(); ++o) nd.out_cnt[(size_t)o] = no;
+        }
+        for (size_t k = 0; k < outputs.size(); ++k) {
+            const DagNode& nd = nodes[(size_t)(outputs[k] >> 2)];
+            const int port = outputs[k] & 3;
+            const size_t c = nd.out_cnt[(size_t)port];
+            if (c) LRB_CHECK(cudaMemcpyAsync(y[k], nd.out_buf[(size_t)port], c * nd.out_size(port), cudaMemcpyDeviceToHost, s));
+            n_out[k] = c;
+        }
+        LRB_CHECK(cudaStreamSynchronize(s));
+        return 0;
+    }
+};
+
 }  // namespace lrb
 
 using namespace lrb;
 
 struct lrb200_graph_s { Graph g; };
+struct lrb200_dag_s { Dag d; };
+namespace lrb { void destroy_graph_handle(void* holder) { delete static_cast<lrb200_graph_s*>(holder); } }
 
 extern "C" {
 
@@ -722,5 +849,63 @@ double lrb200_graph_stage_time_ms(lrb200_graph_t* g, int stage, int* executions)
 }
 
 void lrb200_graph_destroy(lrb200_graph_t* g) { delete g; }
+
+// ---- device DAG ------------------------------------------------------------------------------------------------------
+lrb200_dag_t* lrb200_dag_create(void) {
+    if (lrb200_device_count() <= 0) { set_error("no CUDA device available; libluaradio_b200 has no CPU fallback"); return nullptr; }
+    if (ctx().device < 0 && lrb200_init(0) != 0) return nullptr;
+    lrb200_dag_t* d = new (std::nothrow) lrb200_dag_s();
+    if (!d) set_error("out of memory");
+    return d;
+}
+
+int lrb200_dag_add_block(lrb200_dag_t* d, lrb200_block_t* q, const int* inputs, unsigned num_inputs) {
+    if (!d || !q || !q->impl || (!inputs && num_inputs)) { set_error("dag_add_block: null argument"); return -1; }
+    if (!q->impl->dev_ptrs) { set_error("dag_add_block: block %s was not created with LRB200_DEVICE", q->impl->name); return -1; }
+    const int id = d->d.add(q->impl, nullptr, nullptr, inputs, num_inputs);
+    if (id < 0) return -1;
+    q->impl = nullptr;          // ownership moves to the DAG
+    delete q;
+    return id;
+}
+
+int lrb200_dag_add_graph(lrb200_dag_t* d, lrb200_graph_t* g, int input) {
+    if (!d || !g) { set_error("dag_add_graph: null argument"); return -1; }
+    if (!g->g.committed && g->g.commit(1) != 0) return -1;
+    if (g->g.stages.empty()) { set_error("dag_add_graph: empty graph"); return -1; }
+    return d->d.add(nullptr, &g->g, g, &input, 1);       // on success the handle belongs to the DAG
+}
+
+int lrb200_dag_set_outputs(lrb200_dag_t* d, const int* outputs, unsigned num_outputs) {
+    if (!d || !outputs || !num_outputs) { set_error("dag_set_outputs: null argument"); return -1; }
+    for (unsigned k = 0; k < num_outputs; ++k) {
+        const int r = outputs[k];
+        if (r < 0 || (r >> 2) >= (int)d->d.nodes.size() || (r & 3) >= d->d.nodes[(size_t)(r >> 2)].nout()) { set_error("dag_set_outputs: bad reference %d", r); return -1; }
+    }
+    d->d.outputs.assign(outputs, outputs + num_outputs);
+    return 0;
+}
+
+int lrb200_dag_execute(lrb200_dag_t* d, const void* x, size_t n, void* const* y, size_t* n_out) {
+    if (!d || !y || !n_out || (n && !x)) { set_error("dag_execute: null argument"); return -1; }
+    return d->d.run_host(x, n, y, n_out);
+}
+
+size_t lrb200_dag_max_output(const lrb200_dag_t* d, unsigned output, size_t n) {
+    if (!d || output >= d->d.outputs.size()) return 0;
+    // conservative: no node here produces more samples than its input times the interpolation factors on the way
+    size_t m = n;
+    for (const DagNode& nd : d->d.nodes) { const size_t c = nd.sub ? nd.sub->max_output(n) : nd.blk->max_output(n); if (c > m) m = c; }
+    return m;
+}
+
+int lrb200_dag_reset(lrb200_dag_t* d) {
+    if (!d) { set_error("null dag"); return -1; }
+    return d->d.reset();
+}
+
+const char* lrb200_dag_describe(const lrb200_dag_t* d) { return d ? d->d.desc.c_str() : ""; }
+
+void lrb200_dag_destroy(lrb200_dag_t* d) { delete d; }
 
 }  // extern "C"

@@ -212,7 +212,9 @@ def test_cpu_block_between_two_gpu_runs_and_fanout():
     d = O.Downsampler(2).process(mid)
     close(s1.result(), O.complex_magnitude(d))
     close(s2.result(), O.complex_to_real(d))
-    assert top.describe_gpu_graph().count(";") == 0 and "rot+fir" in top.describe_gpu_graph(), top.describe_gpu_graph()
+    # one fused run before the host block, one device DAG (fan-out) behind it
+    desc = top.describe_gpu_graph()
+    assert "rot+fir" in desc and "dag{" in desc, desc
 
 
 def stereo_mpx(n, rate, rng):
@@ -265,8 +267,21 @@ def test_wbfm_stereo_demodulator_dag():
     f = np.fft.rfftfreq(len(got_l), 1 / rate)
     p700, p2300 = spec[np.argmin(np.abs(f - 700))], spec[np.argmin(np.abs(f - 2300))]
     assert p700 > 10 * p2300, (p700, p2300)
-    # three linear GPU runs became device flow graphs (discriminator -> hilbert, two lowpass -> c2r)
-    assert top.describe_gpu_graph().count(";") >= 2, top.describe_gpu_graph()
+    # the whole demodulator is ONE device DAG; its linear runs (discriminator -> hilbert, two lowpass -> c2r) are fused
+    # flow graphs inside it
+    desc = top.describe_gpu_graph()
+    assert desc.startswith("dag{") and desc.count(";") >= 6, desc
+    # and the host-level scheduling of the same graph (chains + single blocks, a host hop at every junction) agrees
+    src2, sl2, sr2 = radio.ArraySource(x, rate, 50000), radio.ArraySink(), radio.ArraySink()
+    demod2 = radio.WBFMStereoDemodulator()
+    top2 = radio.CompositeBlock()
+    top2.connect(src2, demod2)
+    top2.connect(demod2, "left", sl2, "in")
+    top2.connect(demod2, "right", sr2, "in")
+    top2.run(device_dag=False)
+    assert "dag{" not in top2.describe_gpu_graph()
+    close(sl2.result(), sl.result(), absolute=2e-6)
+    close(sr2.result(), sr.result(), absolute=2e-6)
 
 
 def test_am_synchronous_demodulator_dag():
