@@ -279,3 +279,22 @@ def test_scheduler_plans_maximal_gpu_runs_in_a_dag():
     assert ["FrequencyDiscriminatorBlock", "HilbertTransformBlock"] in runs
     assert runs.count(["LowpassFilterBlock", "ComplexToRealBlock"]) == 2
     assert all(len(r) >= 2 for r in runs)
+    # ... and as a whole it is ONE device DAG: a single external input (the source), two outputs (left, right)
+    dags = top._plan_gpu_dags()
+    assert len(dags) == 1
+    members, ext_in, ext_out = dags[0]
+    assert len(members) == 14 and ext_in.owner.name == "ArraySource"
+    assert [p.owner.name for p in ext_out] == ["FMDeemphasisFilterBlock", "FMDeemphasisFilterBlock"]
+    assert top._plan_gpu_runs({m for m in members}) == []
+    # a straight line is no DAG candidate; two external feeds (top_spec topology) keep the set on the host scheduler
+    for t in (radio.CompositeBlock(),):
+        t.connect(radio.ArraySource(x, 1102500.0), radio.TunerBlock(-250e3, 200e3, 5), radio.FrequencyDiscriminatorBlock(1.25), radio.ArraySink())
+        t._prepare_to_run(initialize=False)
+        assert t._plan_gpu_dags() == []
+    t = radio.CompositeBlock()
+    mixer = radio.MultiplyConjugateBlock()
+    t.connect(radio.ArraySource(x, 1e6), "out", mixer, "in1")
+    t.connect(radio.ArraySource(x, 1e6), "out", mixer, "in2")
+    t.connect(mixer, radio.LowpassFilterBlock(16, 100e3), radio.ArraySink())
+    t._prepare_to_run(initialize=False)
+    assert t._plan_gpu_dags() == []
