@@ -12,6 +12,7 @@
 #include "../../include/lrb200.h"
 #include "common.cuh"
 #include "blocks.h"
+#include "fft32_gen.cuh"
 
 #include <cmath>
 #include <new>
@@ -144,6 +145,60 @@ psd_kernel(const void* __restrict__ xv, const float* __restrict__ window, float*
         float p = fmaf(v.x, v.x, v.y * v.y) * inv_scale;
         if (logarithmic) p = 10.0f * log10f(p);
         y[frame * N + i] = p;
+    }
+}
+
+// ---- PSD of 1024-point frames (the spectrum sinks' default size): one WARP per frame on the register-resident 32 x 32
+// transform of fir_fft.cu -- window at the load, DFT32 over n1, twiddle, one warp-private transpose, DFT32 over n2, and
+// |X_k|^2 / scale written lane-contiguously (k = lane + 32 k2).  No CTA barrier in the frame loop.
+constexpr int PS_WARPS = 4;
+constexpr int PS_XSTRIDE = 33;
+__global__ void __launch_bounds__(PS_WARPS * 32)
+psd1024_kernel(const void* __restrict__ xv, const float* __restrict__ window, float* __restrict__ y, long long frames,
+               int complex_in, float inv_scale, int logarithmic, const float2* __restrict__ tw) {
+    extern __shared__ __align__(16) float2 psm[];
+    float2* s_tw = psm;                                            // [k1][n2] W1024^(k1 n2)
+    float* s_win = reinterpret_cast<float*>(psm + 1024);           // 1024 floats
+    float2* xch = psm + 1024 + 512 + (threadIdx.x >> 5) * (32 * PS_XSTRIDE);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += PS_WARPS * 32) { s_tw[i] = tw[i]; s_win[i] = window[i]; }
+    __syncthreads();
+    const long long wstride = (long long)gridDim.x * PS_WARPS;
+    for (long long f = (long long)blockIdx.x * PS_WARPS + warp; f < frames; f += wstride) {
+        float2 v[32];
+        if (complex_in) {
+            const float2* xb = reinterpret_cast<const float2*>(xv) + f * 1024 + lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                const float2 t = __ldcs(xb + 32 * r);
+                const float w = s_win[32 * r + lane];
+                v[r] = make_float2(t.x * w, t.y * w);
+            }
+        } else {
+            const float* xb = reinterpret_cast<const float*>(xv) + f * 1024 + lane;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = make_float2(__ldcs(xb + 32 * r) * s_win[32 * r + lane], 0.f);
+        }
+        fft32_nat2br<false>(v);
+        __syncwarp();
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            float2 t = v[bitrev5(k1)];
+            if (k1 > 0) t = cmul(t, s_tw[k1 * 32 + lane]);
+            xch[k1 * PS_XSTRIDE + lane] = t;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 32; ++r) v[r] = xch[lane * PS_XSTRIDE + r];
+        fft32_nat2br<false>(v);
+        float* yb = y + f * 1024 + lane;
+#pragma unroll
+        for (int k2 = 0; k2 < 32; ++k2) {
+            const float2 t = v[bitrev5(k2)];
+            float p = fmaf(t.x, t.x, t.y * t.y) * inv_scale;
+            if (logarithmic) p = 10.0f * log10f(p);
+            __stcs(yb + 32 * k2, p);
+        }
     }
 }
 
@@ -443,6 +498,7 @@ struct PsdBlock : Block {
     std::vector<float> h_window;
     float* d_window = nullptr;
     float2* d_tw = nullptr;
+    float2* d_tw1024 = nullptr;      // N == 1024: inter-pass twiddles of the register-resident transform
     PsdBlock(int N_, const float* window, double scale, bool log_, bool cplx_, bool dev)
         : N(N_), cplx(cplx_), logarithmic(log_), inv_scale((float)(1.0 / scale)) {
         name = "psd";
@@ -453,7 +509,7 @@ struct PsdBlock : Block {
         while ((1 << logN) < N) ++logN;
         h_window.assign(window, window + N);
     }
-    ~PsdBlock() override { cudaFree(d_window); cudaFree(d_tw); }
+    ~PsdBlock() override { cudaFree(d_window); cudaFree(d_tw); cudaFree(d_tw1024); }
     int init() override {
         std::vector<float2> tw((size_t)N / 2 + 1);
         for (int k = 0; k < N / 2; ++k)
@@ -462,6 +518,16 @@ struct PsdBlock : Block {
         LRB_CHECK(cudaMalloc(&d_tw, sizeof(float2) * ((size_t)N / 2 + 1)));
         LRB_CHECK(cudaMemcpy(d_window, h_window.data(), sizeof(float) * (size_t)N, cudaMemcpyHostToDevice));
         LRB_CHECK(cudaMemcpy(d_tw, tw.data(), sizeof(float2) * ((size_t)N / 2 + 1), cudaMemcpyHostToDevice));
+        if (N == 1024) {
+            std::vector<float2> t2(1024);
+            for (int a = 0; a < 32; ++a)
+                for (int c = 0; c < 32; ++c) {
+                    const int e = (a * c) % 1024;
+                    t2[(size_t)a * 32 + c] = make_float2((float)std::cos(2 * M_PI * e / 1024.0), (float)(-std::sin(2 * M_PI * e / 1024.0)));
+                }
+            LRB_CHECK(cudaMalloc(&d_tw1024, sizeof(float2) * 1024));
+            LRB_CHECK(cudaMemcpy(d_tw1024, t2.data(), sizeof(float2) * 1024, cudaMemcpyHostToDevice));
+        }
         return 0;
     }
     int run(const void* dx, size_t n, void* dy, size_t* n_out, cudaStream_t s) override {
@@ -470,6 +536,18 @@ struct PsdBlock : Block {
         if (n == 0) return 0;
         const size_t frames = n / (size_t)N;
         if (frames > 2147483647u) { set_error("psd: too many frames in one call"); return -1; }
+        if (N == 1024) {
+            constexpr size_t smem = sizeof(float2) * (1024 + 512 + PS_WARPS * 32 * PS_XSTRIDE);
+            long long ctas = ((long long)frames + PS_WARPS - 1) / PS_WARPS;
+            const long long cap = (long long)ctx().sm_count * 4;
+            if (ctas > cap) ctas = cap;
+            psd1024_kernel<<<(unsigned)ctas, PS_WARPS * 32, smem, s>>>(dx, d_window, (float*)dy, (long long)frames, cplx ? 1 : 0, inv_scale,
+                                                                        logarithmic ? 1 : 0, d_tw1024);
+            count_launch();
+            LRB_CHECK(cudaGetLastError());
+            consumed += n;
+            return 0;
+        }
         psd_kernel<<<(unsigned)frames, 256, sizeof(float2) * (size_t)N, s>>>(dx, d_window, (float*)dy, N, logN, cplx ? 1 : 0,
                                                                               inv_scale, logarithmic ? 1 : 0, d_tw);
         count_launch();
