@@ -142,3 +142,33 @@ def test_fields_and_hooks_the_glue_relies_on_exist_in_the_reference():
     glue = open(os.path.join(LUA, "blocks_patch.lua")).read() + open(os.path.join(LUA, "firfilter_patch.lua")).read()
     for cls in set(re.findall(r"radio\.(\w+Block|\w+Source|\w+Sink)\b", glue)):
         assert re.search(r"\b%s\b" % cls, reg), "%s is not a reference block" % cls
+
+
+def test_glue_parses_as_lua():
+    """Every file of the glue goes through a Lua 5.1 (+ LuaJIT goto) grammar (tests/lua_grammar.py, lark/Earley): a syntax
+    error would stop LuaJIT at require() time.  The grammar itself is validated on files of the reference when the
+    reference tree is present (they must parse), and on a few deliberately broken chunks (they must not)."""
+    import pytest
+    from lark.exceptions import LarkError
+    from tests.lua_grammar import parse_lua
+    for f in lua_files():
+        parse_lua(open(os.path.join(LUA, f)).read())
+    for bad in ("local x = = 1", "function f() return 1", "if x then y = 1 ende", "x = {1, 2", "lib.foo(,)", "for i = 1 do end"):
+        with pytest.raises(LarkError):
+            parse_lua(bad)
+    ref = os.environ.get("LUARADIO_REFERENCE", "/root/reference")
+    if os.path.isdir(ref):
+        for rel in ("radio/blocks/signal/firfilter.lua", "radio/core/composite.lua", "radio/core/block.lua", "radio/core/pipe.lua",
+                    "radio/blocks/signal/pll.lua", "radio/blocks/sources/iqfile.lua", "radio/composites/wbfmstereodemodulator.lua"):
+            parse_lua(open(os.path.join(ref, rel)).read())
+
+
+def test_glue_has_no_undefined_or_accidental_globals():
+    """Scope analysis on the parse tree: every variable the glue reads or writes is a local declared earlier in an enclosing
+    scope (`local`, parameters, `self`, loop variables) or a standard Lua / LuaJIT global -- a misspelled local would be a
+    silent nil global in never-executed Lua."""
+    from tests.lua_grammar import undefined_globals
+    for f in lua_files():
+        assert undefined_globals(open(os.path.join(LUA, f)).read()) == [], f
+    # the analysis does see through to real problems
+    assert undefined_globals("local a = 1\nlocal M = {}\n-- names in a comment: foo(bar)\nfunction M.f(x) return a + x - -typo end") == [("typo", 4)]
