@@ -94,7 +94,8 @@ function M.collapse_gpu_runs(connections)
         if up and is_gpu(up.owner) and next_in_run(up.owner) == b then return up.owner end
         return nil
     end
-    local seen = {}
+    -- plan first, rewrite afterwards: adding keys to a table while pairs() walks it is undefined in Lua
+    local seen, runs = {}, {}
     for input, _ in pairs(connections) do
         local b = input.owner
         if is_gpu(b) and not seen[b] and prev_in_run(b) == nil then
@@ -106,17 +107,18 @@ function M.collapse_gpu_runs(connections)
                 seen[nb] = true
                 nb = next_in_run(nb)
             end
-            if #run >= 2 then
-                local chain = GPUChainBlock(run)
-                chain:differentiate({run[1]:get_input_type()})
-                local first_in, last_out = run[1].inputs[1], run[#run].outputs[1]
-                -- upstream edge now ends at the chain's input; edges inside the run disappear
-                connections[chain.inputs[1]] = connections[first_in]
-                for _, rb in ipairs(run) do connections[rb.inputs[1]] = nil end
-                -- downstream consumers now read the chain's output
-                for _, cin in ipairs(consumers[last_out] or {}) do connections[cin] = chain.outputs[1] end
-            end
+            if #run >= 2 then runs[#runs + 1] = run end
         end
+    end
+    for _, run in ipairs(runs) do
+        local chain = GPUChainBlock(run)
+        chain:differentiate({run[1]:get_input_type()})
+        local first_in, last_out = run[1].inputs[1], run[#run].outputs[1]
+        -- upstream edge now ends at the chain's input; edges inside the run disappear
+        connections[chain.inputs[1]] = connections[first_in]
+        for _, rb in ipairs(run) do connections[rb.inputs[1]] = nil end
+        -- downstream consumers now read the chain's output
+        for _, cin in ipairs(consumers[last_out] or {}) do connections[cin] = chain.outputs[1] end
     end
     return connections
 end

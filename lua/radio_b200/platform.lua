@@ -10,8 +10,9 @@
 -- The declarations are generated from include/lrb200.h (tools/gen_lua_cdef.py -> radio_b200/cdef.lua), and
 -- tests/test_lua_glue.py checks that every lib.lrb200_* call in these files is declared there.
 --
--- NOTE: written for LuaJIT 2.0/2.1; not executed in the build container (no LuaJIT there). The C ABI
--- it binds is exercised from Python ctypes (luaradio_b200/_lib.py) with the same prototypes.
+-- NOTE: written for LuaJIT 2.0/2.1.  There is no LuaJIT in the build container: the logic of these files runs in the
+-- CPU test-suite under a test interpreter with mock radio / ffi / library objects (tests/test_lua_exec.py); the C ABI
+-- they bind is exercised from Python ctypes (luaradio_b200/_lib.py) with the same prototypes.
 
 local ffi = require('ffi')
 local platform = require('radio.core.platform')

@@ -21,7 +21,8 @@ block: stat* laststat?
      | "local" namelist ("=" explist)?                       -> local_assign
      | "goto" NAME                                           -> goto_stat
      | "::" NAME "::"                                        -> label
-laststat: "return" explist? ";"? | "break" ";"?
+laststat: "return" explist? ";"?   -> return_stat
+        | "break" ";"?               -> break_stat
 funcname: NAME ("." NAME)* method?
 method: ":" NAME
 varlist: var ("," var)*
@@ -37,7 +38,7 @@ explist: exp ("," exp)*
 ?mul_exp: unary_exp (MUL_OP unary_exp)*
 ?unary_exp: UNARY_OP unary_exp | MINUS unary_exp | pow_exp
 ?pow_exp: atom ("^" unary_exp)?
-?atom: "nil" | "false" | "true" | NUMBER | STRING | LONGSTRING | "..." | function | prefixexp | tableconstructor
+?atom: NIL | FALSE | TRUE | NUMBER | STRING | LONGSTRING | VARARG | function | prefixexp | tableconstructor
 
 ?prefixexp: var | functioncall | "(" exp ")"
 var: NAME | prefixexp "[" exp "]" | prefixexp "." NAME
@@ -45,12 +46,16 @@ functioncall: prefixexp args | prefixexp ":" NAME args
 args: "(" explist? ")" | tableconstructor | STRING | LONGSTRING
 function: "function" funcbody
 funcbody: "(" parlist? ")" block "end"
-parlist: namelist ("," "...")? | "..."
+parlist: namelist ("," VARARG)? | VARARG
 tableconstructor: "{" fieldlist? "}"
 fieldlist: field (("," | ";") field)* ("," | ";")?
 field: "[" exp "]" "=" exp | NAME "=" exp | exp
 
 CMP_OP: "<=" | ">=" | "==" | "~=" | "<" | ">"
+NIL: "nil"
+FALSE: "false"
+TRUE: "true"
+VARARG: "..."
 PLUS: "+"
 MINUS: "-"
 MUL_OP: "*" | "/" | "%"

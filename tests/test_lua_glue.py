@@ -1,5 +1,5 @@
-"""Static checks of the LuaJIT glue (lua/radio_b200/*.lua).  LuaJIT is not installed in the build image, so the glue is
-never executed here; these tests make it reviewable instead: the FFI declarations are GENERATED from include/lrb200.h
+"""Static checks of the LuaJIT glue (lua/radio_b200/*.lua).  LuaJIT is not installed in the build image (the glue's logic
+is executed under a test interpreter in tests/test_lua_exec.py); these tests make it reviewable as well: the FFI declarations are GENERATED from include/lrb200.h
 and must be current, every lrb200_* symbol the Lua code calls must be declared (LuaJIT raises "missing declaration"
 otherwise), every helper / method it calls must be defined by the glue or be part of the reference's block API, and the
 block structure of every file must balance."""
