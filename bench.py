@@ -73,17 +73,26 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled while the device runs the bench load.
+
+    The timed region of the default run is ~16 ms, shorter than one nvidia-smi period and far shorter than nvidia-smi's own
+    start-up, so: start() launches the sampler BEFORE the warm-up and wait_ready() blocks until its first line arrives;
+    every line is time-stamped on arrival; mark(t0, t1) names the timed region; and when fewer than MIN_LOAD samples fell
+    inside it the caller keeps the identical load running (continue_load) until enough were taken.  The result says how many
+    samples came from the timed region itself and how many from warm-up / continuation of the same step loop."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MIN_LOAD = 4
+    PERIOD_MS = 20
 
     def __init__(self, index=0):
         self.index, self.samples, self.proc = index, [], None
+        self.t_load0 = self.t_load1 = self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -92,33 +101,75 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.monotonic(), line.strip()))
+
+    def wait_ready(self, timeout=8.0):
+        """Block until the first sample line has arrived (nvidia-smi start-up can take a second on an 8-GPU box)."""
+        t_end = time.monotonic() + timeout
+        while self.proc and not self.samples and time.monotonic() < t_end and self.proc.poll() is None:
+            time.sleep(0.01)
+        return bool(self.samples)
+
+    def load_begin(self):
+        self.t_load0 = time.monotonic()
+
+    def mark(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def count_in(self, t0, t1):
+        return sum(1 for t, _ in list(self.samples) if t0 <= t <= t1)
+
+    def continue_load(self, step, sync, budget_s=1.5):
+        """Keep the same step loop running until MIN_LOAD samples were taken under load (or the budget is spent)."""
+        if not self.proc or self.t_load0 is None:
+            return
+        t_end = time.monotonic() + budget_s
+        while self.count_in(self.t_load0, time.monotonic()) < self.MIN_LOAD and time.monotonic() < t_end:
+            for _ in range(8):
+                step()
+            sync()
+        self.t_load1 = time.monotonic()
 
     def stop(self):
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        if self.t_load1 is None:
+            self.t_load1 = time.monotonic()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            f = [t.strip() for t in s.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+        def parse(rows):
+            sm, mx, reasons = [], None, set()
+            for s in rows:
+                f = [t.strip() for t in s.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx = float(f[1])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons
+
+        rows = list(self.samples)
+        lo = self.t_load0 if self.t_load0 is not None else float("-inf")
+        load = [s for t, s in rows if lo <= t <= self.t_load1]
+        timed = [s for t, s in rows if self.t0 is not None and self.t0 <= t <= self.t1]
+        sm, mx, reasons = parse(load)
+        if not sm:                                   # nothing under load: report what there is and say so
+            sm, mx, reasons = parse([s for _, s in rows])
+            reasons = set(reasons) | {"no sample under load"}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(parse(timed)[0]),
+                "period_ms": self.PERIOD_MS,
+                "window": "warm-up + timed region + continuation of the same step loop until >= %d samples" % self.MIN_LOAD}
 
 
 def chain_taps(fu=None):
@@ -277,28 +328,42 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     warm = max(args.warmup, 3)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        sampler.wait_ready()
+    barrier()
+    sampler.load_begin()
     for _ in range(warm):
         step()
     barrier()
     launches0 = lib.lrb200_launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.monotonic()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    sampler.mark(t_host0, time.monotonic())
     ms_total = e0.elapsed_time(e1)
     launches = lib.lrb200_launch_count() - launches0
     tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_step = float(tt.item()) / args.steps
+    # the timed region is shorter than a sampling period: every rank keeps the identical load running (untimed) while
+    # rank 0 collects its clock samples.  N > 1: the same count on every rank (derived from the all-reduced step time), so
+    # that the halo exchange inside step() stays matched across ranks
+    if world > 1:
+        for _ in range(int(min(512, max(16, 120.0 / max(ms_step, 1e-3))))):
+            step()
+        barrier()
+        sampler.t_load1 = time.monotonic()
+    elif rank == 0:
+        sampler.continue_load(step, torch.cuda.synchronize)
+    clocks = sampler.stop() if rank == 0 else None
     value = world * n / (ms_step * 1e-3) / 1e6          # M input-samples/s, whole job
     n_out_step = int(n_out.value)
 

@@ -298,3 +298,38 @@ def test_scheduler_plans_maximal_gpu_runs_in_a_dag():
     t.connect(mixer, radio.LowpassFilterBlock(16, 100e3), radio.ArraySink())
     t._prepare_to_run(initialize=False)
     assert t._plan_gpu_dags() == []
+
+
+def test_bench_clock_sampler_with_a_fake_nvidia_smi(tmp_path, monkeypatch):
+    """bench.ClockSampler against a stand-in `nvidia-smi` on PATH: it must wait for the first line, keep the load loop going
+    until enough samples were taken under load (the timed region is shorter than one sampling period), split the samples
+    into timed-region / load, and report throttle reasons."""
+    import stat
+    import sys
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/sh\nsleep 0.3\nwhile true; do echo '1965, 1965, Not Active, Not Active, Not Active, Active'; sleep 0.02; done\n")
+    fake.chmod(fake.stat().st_mode | stat.S_IEXEC)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    sys.path.insert(0, ROOT)
+    import bench
+    s = bench.ClockSampler(0)
+    s.start()
+    t0 = time.monotonic()
+    assert s.wait_ready() and time.monotonic() - t0 >= 0.25           # blocked through the slow start-up
+    s.load_begin()
+    steps = []
+    th0 = time.monotonic()
+    time.sleep(0.005)                                                  # a "timed region" far shorter than a period
+    s.mark(th0, time.monotonic())
+    s.continue_load(lambda: steps.append(1), lambda: time.sleep(0.01))
+    c = s.stop()
+    assert c["samples"] >= bench.ClockSampler.MIN_LOAD and len(steps) >= 8
+    assert c["sm_mhz"] == 1965.0 and c["sm_max_mhz"] == 1965.0 and c["reasons"] == ["sw_power_cap"]
+    assert c["samples_in_timed_region"] <= 1
+    # no nvidia-smi at all: an explicit reason, never a silent empty record
+    monkeypatch.setenv("PATH", str(tmp_path / "nowhere"))
+    s = bench.ClockSampler(0)
+    s.start()
+    assert not s.wait_ready(timeout=0.2)
+    assert s.stop()["reasons"] == ["nvidia-smi unavailable"]
