@@ -201,6 +201,7 @@ struct InterpFirBlock : Block {       // [MultiplyConstant ->] Upsampler -> FIR(
     float* d_taps = nullptr;
     float* d_taps_tp = nullptr;          // [t][phase] layout for the register-tiled interpolator (D == 1, L <= 8)
     int Tt = 0;
+    bool rs_ok = false;                  // the register-tiled (L, D) polyphase kernel covers this shape (resample.cu)
     void* d_hist[2] = {nullptr, nullptr};
     std::string label;
     InterpFirBlock(bool cdata, const float* taps_host, int ntaps, int interp, int decim, bool has_scale, float scale, bool dev);

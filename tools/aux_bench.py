@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--samples", type=int, default=1 << 28)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--only-resample", action="store_true", help="skip the file-format rows")
     args = ap.parse_args()
     import torch
     import luaradio_b200 as radio
@@ -67,13 +68,14 @@ def main():
         lib.lrb200_graph_destroy(g)
 
     # ---- file formats: fill `raw` with the sink's own output so the source converters read realistic bytes
-    for fmt, b in (("u8", 1), ("s16le", 2), ("f32be", 4)):
+    for fmt, b in (() if args.only_resample else (("u8", 1), ("s16le", 2), ("f32be", 4))):
         timed("iqsink(%s)" % fmt, lambda: [lib.lrb200_iqsink_create(fmt.encode(), D)], xs.data_ptr(), n, raw.data_ptr(), 8 + 2 * b)
         timed("iqconv(%s)" % fmt, lambda: [lib.lrb200_iqconv_create(fmt.encode(), D)], raw.data_ptr(), n, y.data_ptr(), 2 * b + 8)
-    timed("realsink(s16le)", lambda: [lib.lrb200_realsink_create(b"s16le", D)], xs.data_ptr(), 2 * n, raw.data_ptr(), 4 + 2,
-          "WAVFileSink, 16 bits per sample")
+    if not args.only_resample:
+        timed("realsink(s16le)", lambda: [lib.lrb200_realsink_create(b"s16le", D)], xs.data_ptr(), 2 * n, raw.data_ptr(), 4 + 2,
+              "WAVFileSink, 16 bits per sample")
     # ---- resampling family (LowpassFilterBlock(128, 1/L or min(1/L, 1/D), nyquist 1.0) taps)
-    for L, Dn in ((2, 1), (4, 1), (2, 3), (160, 147)):
+    for L, Dn in ((2, 1), (3, 1), (4, 1), (8, 1), (2, 3), (3, 2), (5, 4), (2, 5), (160, 147)):
         m = n // (2 * L) if Dn == 1 else n // 2
         taps = np.array(radio.filter_utils.firwin_lowpass(128, min(1.0 / L, 1.0 / Dn)), np.float32)
 
