@@ -195,6 +195,7 @@ interp_tiled_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __re
 constexpr int RS_THREADS = 128;
 constexpr int RS_C = 4;                       // tap rows per window refill
 constexpr int RS_MAXT = 896;                  // taps incl. zero padding to Tt * L
+constexpr int RS_NPOS = 168;                  // window positions: RI + Tt + 2C <= 20 + 132 + 8
 
 __host__ __device__ constexpr int rs_mod(int a, int m) { return ((a % m) + m) % m; }
 
@@ -205,7 +206,9 @@ struct RsParams {
     long long Mbase, ntiles;                  // first tile's first output (multiple of L, <= m_lo)
     int Tt, Hn, H, HB, NTP;                   // tap rows; history length; tile history (multiple of RI), H / RI; row pitch
     float c;
+    unsigned short pos[RS_NPOS];              // pos[k] = shared-memory index of tile element H + RI - 1 - k (0 once that is negative)
 };
+static_assert(sizeof(RsParams) + 3 * sizeof(void*) <= 4096, "kernel parameters exceed 4 KB");
 
 template <typename T, int L, int D, int RB>
 __global__ void __launch_bounds__(RS_THREADS)
@@ -262,23 +265,18 @@ rs_poly_kernel(const T* __restrict__ x, const T* __restrict__ hist, T* __restric
         const T* St = S + tid;
         // logical W[j] = element H + tid*RI + j - (C-1) - tb*C of the tile: rows t = tb*C + s read W[o_r - s + C - 1]
 #pragma unroll
-        for (int j = 0; j < WN; ++j) {
-            const unsigned ep = (unsigned)(H + j - (C - 1));
-            W[j] = St[(ep % RI) * NTP + ep / RI];
-        }
+        for (int j = 0; j < WN; ++j) W[j] = St[P.pos[RI - 1 + C - 1 - j]];
 #pragma unroll 1
         for (int tb0 = 0; tb0 < nb; tb0 += U) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int tb = tb0 + u;
                 if (tb < nb) {                                   // warp-uniform
-                    if (tb + 1 < nb) {
+                    // unconditional (the table maps the positions past the last row block to a valid address): no inner
+                    // branch, so the loads are scheduled ahead of this block's multiply-adds
+                    const unsigned short* pk = P.pos + (RI - 1 + C - 1) + (tb + 1) * C;
 #pragma unroll
-                        for (int j = 0; j < C; ++j) {
-                            const unsigned ep = (unsigned)(H - (tb + 1) * C - (C - 1) + j);
-                            W[rs_mod(j - (u + 1) * C, WP)] = St[(ep % RI) * NTP + ep / RI];
-                        }
-                    }
+                    for (int j = 0; j < C; ++j) W[rs_mod(j - (u + 1) * C, WP)] = St[pk[-j]];
                     const float* hb = P.h + tb * (C * L);
 #pragma unroll
                     for (int s = 0; s < C; ++s) {
@@ -434,7 +432,7 @@ int InterpFirBlock::init() {
     // the register-tiled (L, D) kernel when the pair is instantiated and the padded taps fit the parameter bank
     if (rs_rb(L, D) > 0) {
         const RsGeom g = rs_geometry(L, D, M, (int)in_size);
-        if (g.Tt * L <= RS_MAXT && g.smem <= 48 * 1024 && g.H <= RS_THREADS) {
+        if (g.Tt * L <= RS_MAXT && g.smem <= 48 * 1024 && g.H <= RS_THREADS && rs_rb(L, D) * D + g.Tt + 2 * RS_C <= RS_NPOS) {
             rs_ok = true;
             if (Hn < g.Tt) Hn = g.Tt;
         }
@@ -465,6 +463,13 @@ int InterpFirBlock::run(const void* dx, size_t n, void* dy, size_t* n_out, cudaS
         const long long TO = (long long)RS_THREADS * rs_rb(L, D) * L;
         P.ntiles = (m_hi - P.Mbase + TO - 1) / TO;
         P.Tt = g.Tt; P.Hn = Hn; P.H = g.H; P.HB = g.HB; P.NTP = g.NTP;
+        {
+            const int RI = rs_rb(L, D) * D;
+            for (int k = 0; k < RS_NPOS; ++k) {
+                const int ep = g.H + RI - 1 - k;
+                P.pos[k] = ep >= 0 ? (unsigned short)((ep % RI) * g.NTP + ep / RI) : (unsigned short)0;
+            }
+        }
         P.c = has_scale ? scale : 1.0f;
 #define LRB_RS(LL, DD) case (LL) * 32 + (DD): \
             if (complex_data) launch_rs<float2, LL, DD>(P, dx, d_hist[cur], dy, g.smem, s); \
