@@ -74,6 +74,45 @@ return function (radio)
     radio.MultiplyConstantBlock.process = b200.process
     radio.MultiplyConstantBlock.process_complex_by_real = b200.process
 
+    -- Two-input element-wise blocks, DelayBlock and PLLBlock (SURVEY 8f row 3: the WBFM stereo / AM synchronous chains).
+    -- multiply.lua:27-28 registers process_complex / process_real per signature; add.lua:32, subtract.lua:32 and
+    -- multiplyconjugate.lua:41,51 define a plain process().
+    local function same_type_out(self) return {self:get_output_type()} end
+    for name, op in pairs({MultiplyBlock = "multiply", MultiplyConjugateBlock = "multiplyconjugate", AddBlock = "add", SubtractBlock = "subtract"}) do
+        b200.install_multi(radio[name], op, function (self, flags)
+            return lib.lrb200_binary_create(op, self:get_input_type() == types.ComplexFloat32 and 1 or 0, flags)
+        end, same_type_out)
+        radio[name].process = b200.process_multi
+    end
+    radio.MultiplyBlock.process_complex = b200.process_multi
+    radio.MultiplyBlock.process_real = b200.process_multi
+    -- radio/blocks/signal/delay.lua:26-60 (ComplexFloat32 / Float32; the Bit and Byte signatures keep the Lua loop)
+    local delay_initialize, delay_process = radio.DelayBlock.initialize, radio.DelayBlock.process
+    b200.install(radio.DelayBlock, "delay", function (self, flags)
+        return lib.lrb200_delay_create(self.num_samples, elem_size(self), flags)
+    end, in_type)
+    local gpu_delay_initialize = radio.DelayBlock.initialize
+    local function float_delay(self)
+        local t = self:get_input_type()
+        return t == types.ComplexFloat32 or t == types.Float32
+    end
+    function radio.DelayBlock:initialize()
+        self.on_gpu = float_delay(self)
+        if self.on_gpu then return gpu_delay_initialize(self) end
+        return delay_initialize(self)
+    end
+    function radio.DelayBlock:process(x)
+        if self.on_gpu then return b200.process(self, x) end
+        return delay_process(self, x)
+    end
+    function radio.DelayBlock:gpu_capable() return float_delay(self) end      -- the scheduler leaves a Bit / Byte delay line on the host
+    -- radio/blocks/signal/pll.lua:113-170: loop constants are derived in the library from the Hz arguments (the reference's
+    -- initialize() overwrites self.loop_bw / freq_min / freq_max with rad/sample; this initialize() leaves them in Hz)
+    b200.install_multi(radio.PLLBlock, "pll", function (self, flags)
+        return lib.lrb200_pll_create(self.loop_bw, self.freq_min, self.freq_max, self.multiplier, self:get_rate(), flags)
+    end, function () return {types.ComplexFloat32, types.Float32} end)
+    radio.PLLBlock.process = b200.process_multi
+
     -- File sample formats (SURVEY 8f row 1).  Sources keep their fread(); the swap + (value - offset)/scale loop of
     -- radio/blocks/sources/iqfile.lua:96-108 / realfile.lua:86-104 becomes one call on the raw chunk.
     local function source_process(create, what)

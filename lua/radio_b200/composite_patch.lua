@@ -4,7 +4,9 @@
 -- backend is active the top block runs through the single-process path (composite.lua:647-707) and every
 -- MAXIMAL LINEAR RUN of GPU blocks in the crawled connection graph is collapsed into ONE lrb200 flow graph:
 -- one process() call per source vector, device-resident intermediates, fused kernels, H2D/D2H only at the
--- two ends of the run.  CPU blocks, multi-input blocks and fan-out points stay ordinary blocks at the edges.
+-- two ends of the run.  Before that, every connected NON-linear set of GPU blocks with a single outside feed (the WBFM
+-- stereo demodulator: two-input blocks, the PLL's two outputs, fan-outs) becomes ONE device DAG (GPUDagBlock, lrb200_dag_*).
+-- CPU blocks, and multi-input blocks or fan-out points outside such a set, stay ordinary blocks at the edges.
 --
 --   local top = radio.CompositeBlock(); top:connect(...); top:run()   -- unchanged user code
 --
@@ -70,9 +72,14 @@ end
 
 local M = {GPUChainBlock = GPUChainBlock}
 
+--- Does `b` have a GPU form in its differentiated type (blocks_patch.lua)?
+local function on_gpu(b)
+    return b.make_device_handle ~= nil and (b.gpu_capable == nil or b:gpu_capable())
+end
+
 --- Is `b` a concrete GPU block that can sit inside a linear run?
 local function is_gpu(b)
-    return b.make_device_handle ~= nil and #b.inputs == 1 and #b.outputs == 1
+    return on_gpu(b) and #b.inputs == 1 and #b.outputs == 1
 end
 
 --- Substitute every maximal linear run (length >= 2) of GPU blocks in the crawled connection map.
@@ -123,6 +130,218 @@ function M.collapse_gpu_runs(connections)
     return connections
 end
 
+--- A connected, NON-linear set of GPU blocks (a two-input block, PLLBlock's two outputs or a fan-out inside the set) fed by
+-- ONE outside output port, as one device DAG (lrb200_dag_*): every edge between the members is a device buffer, the only
+-- host traffic is the set's input and its outputs.  Linear runs inside the set become fused flow graphs
+-- (lrb200_dag_add_graph), everything else single nodes (lrb200_dag_add_block).  A node's output k is referenced as
+-- node * 4 + k, the DAG's own input as -1 (include/lrb200.h).
+local GPUDagBlock = block.factory("GPUDagBlock")
+
+function GPUDagBlock:instantiate(members, ext_in, ext_out, edges)
+    self.blocks, self.ext_in, self.ext_out, self.edges = members, ext_in, ext_out, edges
+    local outputs = {}
+    for k, p in ipairs(ext_out) do outputs[k] = block.Output("out" .. k, p.data_type) end
+    self:add_type_signature({block.Input("in", ext_in.data_type)}, outputs)
+end
+
+function GPUDagBlock:get_rate()
+    return self.ext_out[1].owner:get_rate()
+end
+
+function GPUDagBlock:initialize()
+    local lib = platform.libs.cuda
+    local edges = self.edges                              -- member input port -> producing output port (snapshot)
+    self.dag = ffi.gc(lib.lrb200_dag_create(), lib.lrb200_dag_destroy)
+    if self.dag == nil then b200.fail("dag_create") end
+    local member, consumers = {}, {}
+    for _, b in ipairs(self.blocks) do member[b] = true end
+    for input, output in pairs(edges) do
+        consumers[output] = consumers[output] or {}
+        table.insert(consumers[output], input)
+    end
+    local function simple(b) return #b.inputs == 1 and #b.outputs == 1 end
+    local function next_in_run(b)                         -- the single member consumer of a simple block, if the edge is 1:1
+        local c = consumers[b.outputs[1]]
+        if c and #c == 1 and member[c[1].owner] and simple(c[1].owner) then return c[1].owner end
+        return nil
+    end
+    local ref, done = {}, {}
+    ref[self.ext_in] = -1
+    for _, b in ipairs(self.blocks) do                    -- evaluation (topological) order
+        if not done[b] then
+            local run = {}
+            if simple(b) then
+                run[1] = b
+                local nb = next_in_run(b)
+                while nb and not done[nb] do
+                    run[#run + 1] = nb
+                    nb = next_in_run(nb)
+                end
+            end
+            if #run >= 2 then
+                local g = lib.lrb200_graph_create()
+                if g == nil then b200.fail("graph_create") end
+                for _, rb in ipairs(run) do
+                    if lib.lrb200_graph_append(g, rb:make_device_handle()) ~= 0 then b200.fail("graph_append") end
+                end
+                if lib.lrb200_graph_commit(g, 1) ~= 0 then b200.fail("graph_commit") end
+                local node = lib.lrb200_dag_add_graph(self.dag, g, ref[edges[run[1].inputs[1]]])
+                if node < 0 then
+                    lib.lrb200_graph_destroy(g)
+                    b200.fail("dag_add_graph")
+                end
+                ref[run[#run].outputs[1]] = node * 4
+                for _, rb in ipairs(run) do done[rb] = true end
+            else
+                local ins = ffi.new("int[?]", #b.inputs)
+                for i, p in ipairs(b.inputs) do ins[i - 1] = ref[edges[p]] end
+                local h = b:make_device_handle()
+                local node = lib.lrb200_dag_add_block(self.dag, h, ins, #b.inputs)
+                if node < 0 then
+                    lib.lrb200_block_destroy(h)
+                    b200.fail("dag_add_block")
+                end
+                for k, p in ipairs(b.outputs) do ref[p] = node * 4 + (k - 1) end
+                done[b] = true
+            end
+        end
+    end
+    local outs = ffi.new("int[?]", #self.ext_out)
+    for k, p in ipairs(self.ext_out) do outs[k - 1] = ref[p] end
+    if lib.lrb200_dag_set_outputs(self.dag, outs, #self.ext_out) ~= 0 then b200.fail("dag_set_outputs") end
+    self.outs, self.out_ptrs, self.n_outs = {}, ffi.new("void*[?]", #self.ext_out), ffi.new("size_t[?]", #self.ext_out)
+    for k, p in ipairs(self.ext_out) do self.outs[k] = p.data_type.vector() end
+end
+
+function GPUDagBlock:process(x)
+    local lib = platform.libs.cuda
+    for k, o in ipairs(self.outs) do
+        self.out_ptrs[k - 1] = o:resize(tonumber(lib.lrb200_dag_max_output(self.dag, k - 1, x.length))).data
+    end
+    if lib.lrb200_dag_execute(self.dag, x.data, x.length, self.out_ptrs, self.n_outs) ~= 0 then b200.fail("dag_execute") end
+    for k, o in ipairs(self.outs) do o:resize(tonumber(self.n_outs[k - 1])) end
+    return unpack(self.outs)
+end
+
+M.GPUDagBlock = GPUDagBlock
+
+--- Planning step: the connected sets of GPU blocks that are not a straight line and have exactly one outside feed.
+-- Returns an array of {members = {blocks in evaluation order}, ext_in = OutputPort, ext_out = {OutputPort, ...}}.
+function M.plan_gpu_dags(connections)
+    local gpu, order = {}, {}                             -- set of GPU blocks; all of them in a stable order
+    local function note(b)
+        if not gpu[b] and on_gpu(b) and #b.inputs >= 1 and #b.outputs >= 1 then
+            gpu[b] = true
+            order[#order + 1] = b
+        end
+    end
+    for input, output in pairs(connections) do
+        note(input.owner)
+        note(output.owner)
+    end
+    local adj = {}
+    for _, b in ipairs(order) do adj[b] = {} end
+    for input, output in pairs(connections) do
+        local a, c = input.owner, output.owner
+        if gpu[a] and gpu[c] then
+            adj[a][c] = true
+            adj[c][a] = true
+        end
+    end
+    local seen, plans = {}, {}
+    for _, b in ipairs(order) do
+        if not seen[b] then
+            -- connected component
+            local comp, todo, count = {}, {b}, 0
+            while #todo > 0 do
+                local c = table.remove(todo)
+                if not comp[c] then
+                    comp[c] = true
+                    count = count + 1
+                    for nbr, _ in pairs(adj[c]) do
+                        if not comp[nbr] then todo[#todo + 1] = nbr end
+                    end
+                end
+            end
+            for c, _ in pairs(comp) do seen[c] = true end
+            -- shape: a multi-port member or a fan-out inside the set
+            local nonlinear = false
+            local internal_consumers = {}
+            for input, output in pairs(connections) do
+                if comp[input.owner] and comp[output.owner] then
+                    internal_consumers[output] = (internal_consumers[output] or 0) + 1
+                    if internal_consumers[output] > 1 then nonlinear = true end
+                end
+            end
+            for c, _ in pairs(comp) do
+                if #c.inputs > 1 or #c.outputs > 1 then nonlinear = true end
+            end
+            -- outside feeds and outside readers
+            local feeds, nfeeds, ext_in = {}, 0, nil
+            local read_outside = {}
+            for input, output in pairs(connections) do
+                if comp[input.owner] and not comp[output.owner] and not feeds[output] then
+                    feeds[output] = true
+                    nfeeds = nfeeds + 1
+                    ext_in = output
+                end
+                if comp[output.owner] and not comp[input.owner] then read_outside[output] = true end
+            end
+            if count >= 2 and nonlinear and nfeeds == 1 then
+                -- members in evaluation order: depth-first over the producers inside the set
+                local members, placed = {}, {}
+                local function place(c)
+                    if placed[c] then return end
+                    placed[c] = true
+                    for _, p in ipairs(c.inputs) do
+                        local up = connections[p].owner
+                        if comp[up] then place(up) end
+                    end
+                    members[#members + 1] = c
+                end
+                for _, c in ipairs(order) do
+                    if comp[c] then place(c) end
+                end
+                local ext_out = {}
+                for _, c in ipairs(members) do
+                    for _, p in ipairs(c.outputs) do
+                        if read_outside[p] then ext_out[#ext_out + 1] = p end
+                    end
+                end
+                if #ext_out > 0 then plans[#plans + 1] = {members = members, ext_in = ext_in, ext_out = ext_out} end
+            end
+        end
+    end
+    return plans
+end
+
+--- Substitute every planned set by one GPUDagBlock in the crawled connection map (before the linear runs are collapsed).
+function M.collapse_gpu_dags(connections)
+    local plans = M.plan_gpu_dags(connections)
+    for _, plan in ipairs(plans) do
+        local member, edges = {}, {}
+        for _, b in ipairs(plan.members) do member[b] = true end
+        for _, b in ipairs(plan.members) do
+            for _, p in ipairs(b.inputs) do edges[p] = connections[p] end
+        end
+        local dag = GPUDagBlock(plan.members, plan.ext_in, plan.ext_out, edges)
+        dag:differentiate({plan.ext_in.data_type})
+        -- outside readers of a member output now read the matching DAG output; the members' own edges disappear
+        local rewire = {}
+        for input, output in pairs(connections) do
+            if not member[input.owner] then
+                for k, p in ipairs(plan.ext_out) do
+                    if output == p then rewire[input] = dag.outputs[k] end
+                end
+            end
+        end
+        for input, output in pairs(rewire) do connections[input] = output end
+        for p, _ in pairs(edges) do connections[p] = nil end
+        connections[dag.inputs[1]] = plan.ext_in
+    end
+    return connections
+end
+
 function M.install(radio)
     if not platform.features.cuda then return end
     local CompositeBlock = radio.CompositeBlock
@@ -130,7 +349,10 @@ function M.install(radio)
     function CompositeBlock:_crawl_connections(crawled_connections, composite_stack)
         local top_level = crawled_connections == nil
         local connections = crawl(self, crawled_connections, composite_stack)
-        if top_level then M.collapse_gpu_runs(connections) end
+        if top_level then
+            M.collapse_gpu_dags(connections)
+            M.collapse_gpu_runs(connections)
+        end
         return connections
     end
     function CompositeBlock:start(multiprocess)

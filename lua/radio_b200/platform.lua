@@ -76,4 +76,38 @@ function M.process(self, x)
     return out:resize(tonumber(n_out[0]))
 end
 
+--- Multi-port blocks (two inputs, or PLLBlock's two outputs).  `create(self, flags)` as above; `out_types(self)` returns
+-- the array of output data types.  process(x1, x2, ...) hands one pointer per port to lrb200_block_execute_multi
+-- (radio/core/block.lua:516-532 calls process() with one Vector per input, all of the same length).
+function M.install_multi(class, what, create, out_types)
+    class.gpu_create = create
+    class.gpu_what = what
+    function class:initialize()
+        self.handle = M.own(create(self, M.HOST), what)
+        self.outs = {}
+        for i, t in ipairs(out_types(self)) do self.outs[i] = t.vector() end
+    end
+    function class:make_device_handle()
+        local h = create(self, M.DEVICE)
+        if h == nil then M.fail("Creating lrb200 " .. what .. " object") end
+        return h
+    end
+end
+
+function M.process_multi(self, ...)
+    local lib = platform.libs.cuda
+    local xs = {...}
+    local n = xs[1].length
+    local cap = tonumber(lib.lrb200_block_max_output(self.handle, n))
+    local ins = ffi.new("const void*[?]", #xs)
+    local outs = ffi.new("void*[?]", #self.outs)
+    for i, x in ipairs(xs) do ins[i - 1] = x.data end
+    for i, o in ipairs(self.outs) do outs[i - 1] = o:resize(cap).data end
+    if lib.lrb200_block_execute_multi(self.handle, ins, #xs, n, outs, #self.outs, n_out) ~= 0 then
+        M.fail(self.name)
+    end
+    for _, o in ipairs(self.outs) do o:resize(tonumber(n_out[0])) end
+    return unpack(self.outs)
+end
+
 return M

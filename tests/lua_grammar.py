@@ -71,6 +71,7 @@ COMMENT: /--\[\[.*?\]\]/s | /--\[=\[.*?\]=\]/s | /--[^\n]*/
 """
 
 _parser = None
+_cache = {}
 
 
 def parse_lua(text):
@@ -78,10 +79,13 @@ def parse_lua(text):
     global _parser
     if _parser is None:
         # the BASIC lexer (longest match): with the dynamic one a `-- comment` line can also be read as two unary minuses
-        _parser = Lark(LUA_GRAMMAR, parser="earley", lexer="basic", ambiguity="resolve")
+        _parser = Lark(LUA_GRAMMAR, parser="earley", lexer="basic", ambiguity="resolve", propagate_positions=True)
     if text.startswith("#"):                      # shebang line
         text = "--" + text
-    return _parser.parse(text)
+    tree = _cache.get(text)                       # Earley is slow; the test-suite parses the same glue files many times
+    if tree is None:
+        tree = _cache[text] = _parser.parse(text)
+    return tree
 
 
 LUA_GLOBALS = {"require", "error", "tonumber", "tostring", "ipairs", "pairs", "os", "table", "string", "math", "setmetatable",

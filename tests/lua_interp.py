@@ -153,6 +153,17 @@ class Interp:
                 t.hash[pos] = v
             return []
 
+        def tremove(t, pos=None):
+            n = t.length()
+            if n == 0:
+                return [None]
+            pos = n if pos is None else int(pos)
+            v = t.hash.get(pos)
+            for i in range(pos, n):
+                t.hash[i] = t.hash[i + 1]
+            t.hash.pop(n, None)
+            return [v]
+
         def unpack(t, i=1, j=None):
             j = t.length() if j is None else int(j)
             return [t.hash.get(k) for k in range(int(i), j + 1)]
@@ -167,7 +178,7 @@ class Interp:
 
         import os as _os
         import math as _math
-        table = LuaTable({"insert": tinsert, "unpack": unpack, "concat": lambda t, sep="": [sep.join(self.tostring(x) for x in t.array())]})
+        table = LuaTable({"insert": tinsert, "remove": tremove, "unpack": unpack, "concat": lambda t, sep="": [sep.join(self.tostring(x) for x in t.array())]})
         string = LuaTable({"format": fmt, "len": lambda s: [len(s)], "sub": lambda s, i, j=-1: [s[int(i) - 1:(None if j == -1 else int(j))]]})
         os_t = LuaTable({"getenv": lambda k: [_os.environ.get(k)]})
         math_t = LuaTable({"floor": lambda x: [_math.floor(x)], "min": lambda *a: [min(a)], "max": lambda *a: [max(a)], "huge": float("inf")})
@@ -266,7 +277,13 @@ class Interp:
     def exec_block(self, block, scope):
         sc = Scope(scope)
         for st in block.children:
-            self.exec_stat(st, sc)
+            try:
+                self.exec_stat(st, sc)
+            except LuaError as e:
+                if not getattr(e, "located", False) and isinstance(st, Tree) and getattr(st.meta, "line", None):
+                    e.args = ("%s (line %d)" % (e.args[0], st.meta.line),)
+                    e.located = True
+                raise
 
     def exec_stat(self, st, sc):
         if isinstance(st, Token):

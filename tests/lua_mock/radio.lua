@@ -71,9 +71,30 @@ radio.Source = Source
 local Sink = block.factory("Sink")
 function Sink:instantiate(data_type) self:add_type_signature({block.Input("in", data_type or F)}, {}) end
 radio.Sink = Sink
-local Mixer = block.factory("MultiplyConjugateBlock")
-function Mixer:instantiate() self:add_type_signature({block.Input("in1", C), block.Input("in2", C)}, {block.Output("out", C)}) end
-radio.MultiplyConjugateBlock = Mixer
+-- two-input element-wise blocks: the mock takes the data type as an argument instead of differentiating
+for _, name in ipairs({"MultiplyBlock", "MultiplyConjugateBlock", "AddBlock", "SubtractBlock"}) do
+    local class = block.factory(name)
+    function class:instantiate(data_type)
+        local t = data_type or C
+        self:add_type_signature({block.Input("in1", t), block.Input("in2", t)}, {block.Output("out", t)})
+    end
+    radio[name] = class
+end
+-- DelayBlock keeps a host implementation (the glue falls back to it for the Bit / Byte signatures)
+local Delay = block.factory("DelayBlock")
+function Delay:instantiate(num_samples, data_type)
+    self.num_samples = num_samples
+    self:add_type_signature({block.Input("in", data_type or C)}, {block.Output("out", data_type or C)})
+end
+function Delay:initialize() self.host_initialized = true end
+function Delay:process(x) self.host_processed = (self.host_processed or 0) + 1 return x end
+radio.DelayBlock = Delay
+local PLL = block.factory("PLLBlock")
+function PLL:instantiate(loop_bandwidth, frequency_min, frequency_max, multiplier)
+    self.loop_bw, self.freq_min, self.freq_max, self.multiplier = loop_bandwidth, frequency_min, frequency_max, multiplier or 1.0
+    self:add_type_signature({block.Input("in", C)}, {block.Output("out", C), block.Output("error", F)})
+end
+radio.PLLBlock = PLL
 
 -- CompositeBlock: _crawl_connections returns the stored flat map on the top-level call; start records its argument
 local Composite = block.factory("CompositeBlock")

@@ -35,10 +35,10 @@ class MockLib:
     declaration" otherwise); every call is logged as (name, args)."""
 
     def __init__(self, declared):
-        self._declared, self.calls, self.fail_next_create = declared, [], False
+        self._declared, self.calls, self.fail_next_create, self.dag_nodes = declared, [], False, 0
 
     def __getattr__(self, name):
-        if name.startswith("_") or name in ("calls", "fail_next_create"):
+        if name.startswith("_") or name in ("calls", "fail_next_create", "dag_nodes"):
             raise AttributeError(name)
         if name not in self._declared:
             raise LuaError("missing declaration for symbol '%s'" % name)
@@ -55,7 +55,20 @@ class MockLib:
             if name == "lrb200_last_error":
                 return ["mock error text"]
             if name.endswith("max_output"):
-                return [args[-1] if name.startswith("lrb200_block") or name.startswith("lrb200_graph") else 0]
+                return [args[-1]]
+            if name in ("lrb200_dag_add_graph", "lrb200_dag_add_block"):
+                self.dag_nodes += 1
+                return [self.dag_nodes - 1]
+            if name == "lrb200_dag_execute":
+                for k in list(args[4].hash):
+                    if isinstance(k, int):
+                        args[4].hash[k] = args[2]
+                args[4].hash[0] = args[2]
+                args[4].hash[1] = args[2]
+                return [0]
+            if name == "lrb200_block_execute_multi":
+                args[6].hash[0] = args[3]
+                return [0]
             if name in ("lrb200_block_execute", "lrb200_graph_execute"):
                 args[4].hash[0] = args[2]
                 return [0]
@@ -86,7 +99,7 @@ def make_env(cuda=True):
         t.hash["vector"] = vector
         return t
 
-    types = LuaTable({"ComplexFloat32": make_type("ComplexFloat32"), "Float32": make_type("Float32")})
+    types = LuaTable({"ComplexFloat32": make_type("ComplexFloat32"), "Float32": make_type("Float32"), "Bit": make_type("Bit")})
     cdefs = []
     ffi_c = LuaTable({"fwrite": lambda data, size, n, f: [n], "fread": lambda data, size, n, f: [n], "feof": lambda f: [0]})
     ffi = LuaTable({
@@ -303,7 +316,8 @@ def export_graph(it, radio, types, top, lua_gpu):
         # the fields the create callbacks read
         for k, v in (("taps", vec(types, "Float32", 16)), ("offset", 1e5), ("rate", 1e6), ("gain", 1.0), ("factor", 2),
                      ("b_taps", vec(types, "Float32", 2)), ("a_taps", vec(types, "Float32", 2)), ("hilbert_taps", vec(types, "Float32", 9)),
-                     ("constant", LuaTable({"value": 1.0}))):
+                     ("constant", LuaTable({"value": 1.0})), ("num_samples", 129), ("loop_bw", 100.0), ("freq_min", 18950.0),
+                     ("freq_max", 19050.0), ("multiplier", 2.0)):
             lb.hash[k] = v
         lua_of[b] = lb
     for inp, outp in top._all_connections.items():
@@ -322,6 +336,8 @@ LUA_GPU_BASE = {
     "IIRFilterBlock": "IIRFilterBlock", "FMDeemphasisFilterBlock": "IIRFilterBlock", "SinglepoleLowpassFilterBlock": "IIRFilterBlock",
     "SinglepoleHighpassFilterBlock": "IIRFilterBlock", "HilbertTransformBlock": "HilbertTransformBlock",
     "ComplexMagnitudeBlock": "ComplexMagnitudeBlock", "ComplexToRealBlock": "ComplexToRealBlock", "MultiplyConstantBlock": "MultiplyConstantBlock",
+    "MultiplyBlock": "MultiplyBlock", "MultiplyConjugateBlock": "MultiplyConjugateBlock", "AddBlock": "AddBlock", "SubtractBlock": "SubtractBlock",
+    "DelayBlock": "DelayBlock", "PLLBlock": "PLLBlock",
 }
 
 
@@ -499,3 +515,202 @@ def test_glue_is_inert_without_the_cuda_feature(monkeypatch):
     it.call(it.require("radio_b200.blocks_patch"), [radio])
     assert radio.hash["FIRFilterBlock"].hash == before and lib.calls == []
     assert "make_device_handle" not in radio.hash["DownsamplerBlock"].hash
+
+
+def test_multi_port_block_patches(monkeypatch):
+    """Multiply / MultiplyConjugate / Add / Subtract, DelayBlock and PLLBlock: create arguments, the execute_multi call of the
+    shared multi-port process(), DelayBlock's host fallback for the Bit signature."""
+    it, lib, types, radio = patched_radio(monkeypatch)
+    C, F, B = types.hash["ComplexFloat32"], types.hash["Float32"], types.hash["Bit"]
+    new = lambda cls, *a: it.call(radio.hash[cls], list(a))[0]
+    meth = lambda obj, name, *a: it.call(it.index(obj, name), [obj] + list(a))
+    b200 = it.require("radio_b200.platform")
+    for cls, op in (("MultiplyBlock", "multiply"), ("MultiplyConjugateBlock", "multiplyconjugate"), ("AddBlock", "add"), ("SubtractBlock", "subtract")):
+        for t, flag in ((C, 1), (F, 0)):
+            lib.calls.clear()
+            b = new(cls, t)
+            meth(b, "initialize")
+            assert lib.calls == [("lrb200_binary_create", (op, flag, 0))], cls
+            assert b.hash["outs"].length() == 1 and b.hash["outs"].hash[1].hash["data_type"] is t
+            lib.calls.clear()
+            meth(b, "make_device_handle")
+            assert lib.calls == [("lrb200_binary_create", (op, flag, 1))]
+        assert radio.hash[cls].hash["process"] is b200.hash["process_multi"]
+    assert radio.hash["MultiplyBlock"].hash["process_complex"] is b200.hash["process_multi"]
+    assert radio.hash["MultiplyBlock"].hash["process_real"] is b200.hash["process_multi"]
+    # process(x, y)
+    b = new("MultiplyConjugateBlock", C)
+    meth(b, "initialize")
+    lib.calls.clear()
+    x, y = vec(types, "ComplexFloat32", 512), vec(types, "ComplexFloat32", 512)
+    y.hash["data"] = "second*"
+    out = meth(b, "process", x, y)
+    assert [c[0] for c in lib.calls] == ["lrb200_block_max_output", "lrb200_block_execute_multi"]
+    h, ins, nin, n, outs, nout, _ = lib.calls[1][1]
+    assert h is b.hash["handle"] and (nin, n, nout) == (2, 512, 1)
+    assert (ins.hash[0], ins.hash[1]) == (x.hash["data"], "second*") and outs.hash[0] == out[0].hash["data"]
+    assert len(out) == 1 and out[0].hash["length"] == 512
+    # DelayBlock: float types on the GPU, Bit on the host
+    lib.calls.clear()
+    d = new("DelayBlock", 129, C)
+    meth(d, "initialize")
+    assert lib.calls == [("lrb200_delay_create", (129, 8, 0))] and meth(d, "gpu_capable") == [True]
+    meth(d, "process", x)
+    assert [c[0] for c in lib.calls][1:] == ["lrb200_block_max_output", "lrb200_block_execute"]
+    lib.calls.clear()
+    d = new("DelayBlock", 5, F)
+    meth(d, "make_device_handle")
+    assert lib.calls == [("lrb200_delay_create", (5, 4, 1))]
+    lib.calls.clear()
+    d = new("DelayBlock", 7, B)
+    meth(d, "initialize")
+    meth(d, "process", x)
+    assert lib.calls == [] and d.hash["host_initialized"] is True and d.hash["host_processed"] == 1
+    assert meth(d, "gpu_capable") == [False]
+    # PLLBlock: Hz arguments and the block's rate; two outputs
+    lib.calls.clear()
+    p = new("PLLBlock", 100.0, 18950.0, 19050.0, 2.0)
+    p.hash["rate"] = 220500.0
+    meth(p, "initialize")
+    assert lib.calls == [("lrb200_pll_create", (100.0, 18950.0, 19050.0, 2.0, 220500.0, 0))]
+    lib.calls.clear()
+    out = meth(p, "process", x)
+    assert len(out) == 2 and out[0].hash["data_type"] is C and out[1].hash["data_type"] is F
+    assert lib.calls[1][0] == "lrb200_block_execute_multi" and lib.calls[1][1][2:6:3] == (1, 2)
+    p = new("PLLBlock", 100.0, 18950.0, 19050.0)
+    p.hash["rate"] = 1.0
+    meth(p, "make_device_handle")
+    assert lib.calls[-1][1][3] == 1.0 and lib.calls[-1][1][5] == 1            # default multiplier; DEVICE pointers
+
+
+def dag_topologies():
+    import luaradio_b200 as radio
+    x = np.zeros(16, np.complex64)
+    tops = dict(topologies())
+    top = radio.CompositeBlock()
+    top.connect(radio.ArraySource(x, 1e6), radio.AMSynchronousDemodulator(100e3, 5e3), radio.ArraySink())
+    top._prepare_to_run(initialize=False)
+    tops["am_synchronous"] = top
+    return tops
+
+
+@pytest.mark.parametrize("name", ["stereo", "am_synchronous", "mono", "two_sources", "host_and_fanout"])
+def test_lua_dag_planner_matches_the_python_planner(monkeypatch, name):
+    """plan_gpu_dags / collapse_gpu_dags (Lua, executed) against CompositeBlock._plan_gpu_dags (Python): same member sets,
+    same outside feed, same outside-read outputs; the rewritten map is consistent; no linear run is left among the members."""
+    it, lib, types, radio = patched_radio(monkeypatch)
+    top = dag_topologies()[name]
+    lua_gpu = {b: LUA_GPU_BASE[b.name] for b in top._concrete_order if b.name in LUA_GPU_BASE}
+    from luaradio_b200.signal_blocks import GPUBlock
+    assert all(b in lua_gpu for b in top._concrete_order if isinstance(b, GPUBlock) and b.inputs and b.outputs), "a Python GPU block without a Lua form"
+    expected = top._plan_gpu_dags()
+    lua_of, conns = export_graph(it, radio, types, top, lua_gpu)
+    name_of = {id(lb): b for b, lb in lua_of.items()}
+    patch = it.require("radio_b200.composite_patch")
+    plans = it.call(patch.hash["plan_gpu_dags"], [conns])[0].array()
+    assert len(plans) == len(expected)
+    assert (expected == []) == (name in ("mono", "two_sources"))          # host_and_fanout: Downsampler -> {ComplexMagnitude, ComplexToReal}
+    if not expected:
+        return
+    (members_py, ext_in_py, ext_out_py), plan = expected[0], plans[0]
+    members = plan.hash["members"].array()
+    assert {id(m) for m in members} == {id(lua_of[b]) for b in members_py} and len(members) == len(members_py)
+    assert name_of[id(plan.hash["ext_in"].hash["owner"])] is ext_in_py.owner
+    assert sorted(name_of[id(p.hash["owner"])].name for p in plan.hash["ext_out"].array()) == sorted(p.owner.name for p in ext_out_py)
+    # evaluation order: every member comes after the members that feed it
+    index = {id(m): k for k, m in enumerate(members)}
+    for m in members:
+        for p in m.hash["inputs"].array():
+            up = conns.hash[p].hash["owner"]
+            if id(up) in index:
+                assert index[id(up)] < index[id(m)]
+    # rewrite
+    before = dict(conns.hash)
+    it.call(patch.hash["collapse_gpu_dags"], [conns])
+    dags = {id(o.hash["owner"]): o.hash["owner"] for o in conns.hash.values() if "ext_out" in o.hash["owner"].hash}
+    assert len(dags) == 1
+    dag = next(iter(dags.values()))
+    member_ids = {id(m) for m in members}
+    for i, o in conns.hash.items():
+        assert id(i.hash["owner"]) not in member_ids and id(o.hash["owner"]) not in member_ids
+    assert conns.hash[dag.hash["inputs"].hash[1]] is plan.hash["ext_in"]
+    ext_out = plan.hash["ext_out"].array()
+    for i, o in before.items():
+        if id(i.hash["owner"]) in member_ids:
+            continue
+        if id(o.hash["owner"]) in member_ids:
+            k = [id(p) for p in ext_out].index(id(o))
+            assert conns.hash[i] is dag.hash["outputs"].hash[k + 1]
+            assert dag.hash["outputs"].hash[k + 1].hash["data_type"] is o.hash["data_type"]
+        else:
+            assert conns.hash[i] is o
+    # the chain planner then finds nothing among what is left (stereo / AM synchronous: source -> dag -> sinks)
+    n_before = len(conns.hash)
+    it.call(patch.hash["collapse_gpu_runs"], [conns])
+    chains = {id(o.hash["owner"]): o.hash["owner"] for o in conns.hash.values() if "blocks" in o.hash["owner"].hash and "ext_out" not in o.hash["owner"].hash}
+    if name == "host_and_fanout":           # the run in front of the host block is still a chain of its own
+        assert [[b.hash["name"] for b in c.hash["blocks"].array()] for c in chains.values()] == [["FrequencyTranslatorBlock", "LowpassFilterBlock"]]
+    else:
+        assert len(conns.hash) == n_before and not chains
+    py_runs = [[b.name for b in run] for run, _, _ in top._plan_gpu_runs({m for m in members_py})]
+    assert py_runs == ([["FrequencyTranslatorBlock", "LowpassFilterBlock"]] if name == "host_and_fanout" else [])
+
+
+@pytest.mark.parametrize("name", ["stereo", "am_synchronous"])
+def test_dag_block_builds_a_valid_device_dag(monkeypatch, name):
+    """GPUDagBlock:initialize() against the mock library: dag_create, then nodes whose input references are -1 (the DAG's
+    input) or node * 4 + k of an EARLIER node with that many outputs; every member lands in exactly one node; linear runs
+    inside the set are committed as fused flow graphs; set_outputs names valid references; process() returns one vector per
+    outside-read output."""
+    it, lib, types, radio = patched_radio(monkeypatch)
+    top = dag_topologies()[name]
+    lua_gpu = {b: LUA_GPU_BASE[b.name] for b in top._concrete_order if b.name in LUA_GPU_BASE}
+    lua_of, conns = export_graph(it, radio, types, top, lua_gpu)
+    patch = it.require("radio_b200.composite_patch")
+    it.call(patch.hash["collapse_gpu_dags"], [conns])
+    dag = next(o.hash["owner"] for o in conns.hash.values() if "ext_out" in o.hash["owner"].hash)
+    meth = lambda obj, nm, *a: it.call(it.index(obj, nm), [obj] + list(a))
+    lib.calls.clear()
+    lib.dag_nodes = 0
+    meth(dag, "initialize")
+    assert lib.calls[0][0] == "lrb200_dag_create"
+    d = dag.hash["dag"]
+    n_members = dag.hash["blocks"].length()
+    node_outputs, placed, pending_graph = [], 0, {}
+    for nm, args in lib.calls[1:]:
+        if nm == "lrb200_graph_append":
+            pending_graph[id(args[0])] = pending_graph.get(id(args[0]), 0) + 1
+            assert args[1].args[-1] == 1                               # DEVICE pointers
+        elif nm == "lrb200_graph_commit":
+            assert args[1] == 1 and pending_graph[id(args[0])] >= 2
+        elif nm == "lrb200_dag_add_graph":
+            assert args[0] is d
+            ref = args[2]
+            assert ref == -1 or (ref // 4 < len(node_outputs) and ref % 4 < node_outputs[ref // 4])
+            node_outputs.append(1)
+            placed += pending_graph.pop(id(args[1]))
+        elif nm == "lrb200_dag_add_block":
+            assert args[0] is d and args[1].args[-1] == 1
+            for k in range(args[3]):
+                ref = args[2].hash[k]
+                assert ref == -1 or (ref // 4 < len(node_outputs) and ref % 4 < node_outputs[ref // 4]), (nm, ref)
+            node_outputs.append(2 if args[1].what == "lrb200_pll_create" else 1)
+            assert args[3] == (2 if args[1].what == "lrb200_binary_create" else 1)
+            placed += 1
+    assert placed == n_members and not pending_graph
+    assert any(c[0] == "lrb200_dag_add_graph" for c in lib.calls)      # the linear runs inside the set are fused graphs
+    so = [c for c in lib.calls if c[0] == "lrb200_dag_set_outputs"]
+    n_ext = dag.hash["ext_out"].length()
+    assert len(so) == 1 and so[0][1][2] == n_ext
+    for k in range(n_ext):
+        ref = so[0][1][1].hash[k]
+        assert ref >= 0 and ref // 4 < len(node_outputs) and ref % 4 < node_outputs[ref // 4]
+    assert lib.calls[-1][0] == "lrb200_dag_set_outputs"
+    # process
+    lib.calls.clear()
+    x = vec(types, "ComplexFloat32", 4096)
+    outs = meth(dag, "process", x)
+    assert len(outs) == n_ext and all(o.hash["length"] == 4096 for o in outs)
+    assert [c[0] for c in lib.calls] == ["lrb200_dag_max_output"] * n_ext + ["lrb200_dag_execute"]
+    assert lib.calls[-1][1][:3] == (d, x.hash["data"], 4096)
+    assert meth(dag, "get_rate") == [1e6]
