@@ -123,6 +123,15 @@ GLUE_RELIES_ON = [
     ("radio/core/composite.lua", "function CompositeBlock:_crawl_connections"), ("radio/core/composite.lua", "function CompositeBlock:start"),
     ("radio/core/composite.lua", "function CompositeBlock:_connect_pipes"), ("radio/core/block.lua", "function Block:differentiate"),
     ("radio/core/platform.lua", "platform.load"), ("radio/core/pipe.lua", "function Pipe:write"),
+    # multi-port blocks
+    ("radio/blocks/signal/multiply.lua", "MultiplyBlock.process_complex"), ("radio/blocks/signal/multiply.lua", "MultiplyBlock.process_real"),
+    ("radio/blocks/signal/multiplyconjugate.lua", "function MultiplyConjugateBlock:process(x, y)"),
+    ("radio/blocks/signal/add.lua", "function AddBlock:process(x, y)"), ("radio/blocks/signal/subtract.lua", "function SubtractBlock:process(x, y)"),
+    ("radio/blocks/signal/delay.lua", "self.num_samples"), ("radio/blocks/signal/delay.lua", "function DelayBlock:initialize"),
+    ("radio/blocks/signal/delay.lua", "types.Bit"),
+    ("radio/blocks/signal/pll.lua", "self.loop_bw"), ("radio/blocks/signal/pll.lua", "self.freq_min"), ("radio/blocks/signal/pll.lua", "self.freq_max"),
+    ("radio/blocks/signal/pll.lua", "self.multiplier"), ("radio/blocks/signal/pll.lua", "return out, err"),
+    ("radio/core/block.lua", "self.outputs[i].data_type"), ("radio/core/block.lua", "self.inputs[i].data_type"),
 ]
 
 
@@ -140,7 +149,7 @@ def test_fields_and_hooks_the_glue_relies_on_exist_in_the_reference():
     # every class the glue patches is registered by the reference (radio/blocks/init.lua, radio/composites/init.lua)
     reg = open(os.path.join(ref, "radio/blocks/init.lua")).read()
     glue = open(os.path.join(LUA, "blocks_patch.lua")).read() + open(os.path.join(LUA, "firfilter_patch.lua")).read()
-    for cls in set(re.findall(r"radio\.(\w+Block|\w+Source|\w+Sink)\b", glue)):
+    for cls in set(re.findall(r"radio\.(\w+Block|\w+Source|\w+Sink)\b", glue)) | set(re.findall(r"\b(\w+Block) = \"", glue)):
         assert re.search(r"\b%s\b" % cls, reg), "%s is not a reference block" % cls
 
 
