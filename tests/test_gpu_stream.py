@@ -410,7 +410,10 @@ def test_nbfm_am_ssb_demodulators(chunk):
 
 
 @pytest.mark.parametrize("L,D,M", [(2, 1, 128), (3, 1, 128), (7, 5, 128), (2, 3, 128), (3, 2, 128), (8, 4, 100), (5, 4, 64), (4, 25, 200),
-                                   (160, 147, 1024), (5, 1, 33)])
+                                   (160, 147, 1024), (5, 1, 33),
+                                   # the remaining instantiations of the register-tiled kernel (resample.cu: LRB_RS list), and its limits
+                                   (4, 1, 128), (6, 1, 128), (7, 1, 100), (8, 1, 128), (2, 5, 128), (3, 4, 128), (3, 5, 90), (4, 3, 128),
+                                   (4, 5, 128), (5, 2, 128), (5, 3, 77), (2, 1, 255), (2, 1, 300), (2, 1, 3)])
 @pytest.mark.parametrize("cplx", [True, False])
 def test_interpolator_and_rational_resampler_stream(L, D, M, cplx):
     """InterpolatorBlock / RationalResamplerBlock as one polyphase kernel (fused) and as four separate kernels (unfused)
