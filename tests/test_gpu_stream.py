@@ -410,10 +410,7 @@ def test_nbfm_am_ssb_demodulators(chunk):
 
 
 @pytest.mark.parametrize("L,D,M", [(2, 1, 128), (3, 1, 128), (7, 5, 128), (2, 3, 128), (3, 2, 128), (8, 4, 100), (5, 4, 64), (4, 25, 200),
-                                   (160, 147, 1024), (5, 1, 33),
-                                   # the remaining instantiations of the register-tiled kernel (resample.cu: LRB_RS list), and its limits
-                                   (4, 1, 128), (6, 1, 128), (7, 1, 100), (8, 1, 128), (2, 5, 128), (3, 4, 128), (3, 5, 90), (4, 3, 128),
-                                   (4, 5, 128), (5, 2, 128), (5, 3, 77), (2, 1, 255), (2, 1, 300), (2, 1, 3)])
+                                   (160, 147, 1024), (5, 1, 33)])
 @pytest.mark.parametrize("cplx", [True, False])
 def test_interpolator_and_rational_resampler_stream(L, D, M, cplx):
     """InterpolatorBlock / RationalResamplerBlock as one polyphase kernel (fused) and as four separate kernels (unfused)
@@ -433,3 +430,16 @@ def test_interpolator_and_rational_resampler_stream(L, D, M, cplx):
             assert "upsample+fir" in top.describe_gpu_graph() and top.describe_gpu_graph().count("|") == 0, top.describe_gpu_graph()
         else:
             assert top.describe_gpu_graph().count("|") == (3 if D > 1 else 2), top.describe_gpu_graph()
+
+
+# The remaining instantiations of the register-tiled kernel (resample.cu: the LRB_RS list) and its tap-count limits
+# (M = 255 is the largest the x2 shape takes, 300 falls back to the round-1 kernel).  Added after the round's GPU budget was
+# spent: they passed through the numpy model of the kernel on the CPU (tests/test_resampler_model.py) but have NOT run on a
+# GPU yet, hence non-strict xfail -- an XPASS in the next GPU run is the cue to fold them into the list above.
+@pytest.mark.xfail(strict=False, reason="not yet run on a GPU (added after the round's GPU budget ended); CPU model of the kernel passes")
+@pytest.mark.parametrize("L,D,M", [(4, 1, 128), (6, 1, 128), (7, 1, 100), (8, 1, 128), (2, 5, 128), (3, 4, 128), (3, 5, 90), (4, 3, 128),
+                                   (4, 5, 128), (5, 2, 128), (5, 3, 77), (2, 1, 255), (2, 1, 300), (2, 1, 3)])
+@pytest.mark.parametrize("cplx", [True, False])
+def test_resampler_remaining_instantiations(L, D, M, cplx):
+    test_interpolator_and_rational_resampler_stream(L, D, M, cplx)
+
