@@ -10,9 +10,11 @@
 --
 --   local top = radio.CompositeBlock(); top:connect(...); top:run()   -- unchanged user code
 --
--- install(radio) wraps two methods of CompositeBlock:
+-- install(radio) wraps four methods of CompositeBlock:
 --   _crawl_connections (composite.lua:343-381)  the top-level call returns the flat input-port -> output-port map;
---                                               GPU runs are substituted there, before _connect_pipes (:383-393)
+--                                               GPU sub-graphs are substituted there, before _connect_pipes (:383-393)
+--   _connect_pipes (composite.lua:383-393)      members of a sub-graph get a rate-only link in place of their pipe
+--   _initialize (composite.lua:416-424)         initialises the substitutes after the original blocks
 --   start (composite.lua:534-545)               forces multiprocess = false
 -- Set LUARADIO_B200_SUPERCHUNK=<samples> to pack the per-vector calls into pinned super-chunks
 -- (lrb200_graph_set_superchunk): throughput of the reference's 8192-sample vectors goes from launch-bound to
@@ -26,8 +28,9 @@ local b200 = require('radio_b200.platform')
 --- A block that stands for a run of connected GPU blocks [first .. last].
 local GPUChainBlock = block.factory("GPUChainBlock")
 
-function GPUChainBlock:instantiate(blocks)
+function GPUChainBlock:instantiate(blocks, edges)
     self.blocks = blocks
+    self.edges = edges or {}                 -- member input port -> the output port that fed it in the crawled graph
     self:add_type_signature({block.Input("in", blocks[1]:get_input_type())},
                             {block.Output("out", blocks[#blocks]:get_output_type())})
 end
@@ -84,7 +87,7 @@ end
 
 --- Substitute every maximal linear run (length >= 2) of GPU blocks in the crawled connection map.
 -- connections: InputPort -> OutputPort over concrete blocks (composite.lua:343-381).
-function M.collapse_gpu_runs(connections)
+function M.collapse_gpu_runs(connections, substitutes)
     -- consumers per output port
     local consumers = {}
     for input, output in pairs(connections) do
@@ -118,8 +121,11 @@ function M.collapse_gpu_runs(connections)
         end
     end
     for _, run in ipairs(runs) do
-        local chain = GPUChainBlock(run)
+        local edges = {}
+        for _, rb in ipairs(run) do edges[rb.inputs[1]] = connections[rb.inputs[1]] end
+        local chain = GPUChainBlock(run, edges)
         chain:differentiate({run[1]:get_input_type()})
+        if substitutes then substitutes[#substitutes + 1] = chain end
         local first_in, last_out = run[1].inputs[1], run[#run].outputs[1]
         -- upstream edge now ends at the chain's input; edges inside the run disappear
         connections[chain.inputs[1]] = connections[first_in]
@@ -316,7 +322,7 @@ function M.plan_gpu_dags(connections)
 end
 
 --- Substitute every planned set by one GPUDagBlock in the crawled connection map (before the linear runs are collapsed).
-function M.collapse_gpu_dags(connections)
+function M.collapse_gpu_dags(connections, substitutes)
     local plans = M.plan_gpu_dags(connections)
     for _, plan in ipairs(plans) do
         local member, edges = {}, {}
@@ -326,6 +332,7 @@ function M.collapse_gpu_dags(connections)
         end
         local dag = GPUDagBlock(plan.members, plan.ext_in, plan.ext_out, edges)
         dag:differentiate({plan.ext_in.data_type})
+        if substitutes then substitutes[#substitutes + 1] = dag end
         -- outside readers of a member output now read the matching DAG output; the members' own edges disappear
         local rewire = {}
         for input, output in pairs(connections) do
@@ -346,14 +353,37 @@ function M.install(radio)
     if not platform.features.cuda then return end
     local CompositeBlock = radio.CompositeBlock
     local crawl, start = CompositeBlock._crawl_connections, CompositeBlock.start
+    local connect_pipes, initialize = CompositeBlock._connect_pipes, CompositeBlock._initialize
+    -- _prepare_to_run (composite.lua:426-466) = _differentiate, _crawl_connections, _connect_pipes(all_connections),
+    -- _validate_rates, _initialize, then the global evaluation order and the control sockets from all_connections.
+    -- _validate_rates and _initialize walk the ORIGINAL blocks (self._connections), the run loop walks all_connections.
     function CompositeBlock:_crawl_connections(crawled_connections, composite_stack)
         local top_level = crawled_connections == nil
         local connections = crawl(self, crawled_connections, composite_stack)
         if top_level then
-            M.collapse_gpu_dags(connections)
-            M.collapse_gpu_runs(connections)
+            self._b200_substitutes = {}
+            M.collapse_gpu_dags(connections, self._b200_substitutes)
+            M.collapse_gpu_runs(connections, self._b200_substitutes)
         end
         return connections
+    end
+    function CompositeBlock:_connect_pipes(all_connections)
+        connect_pipes(self, all_connections)
+        -- the members of a sub-graph have no pipes any more, but _validate_rates (composite.lua:394-414) and the members'
+        -- own initialize() (LowpassFilterBlock:initialize -> self:get_rate(), block.lua:383-390) ask their input pipe for
+        -- the rate: a rate-only link to the port that fed the member in the crawled graph
+        for _, sub in ipairs(self._b200_substitutes or {}) do
+            for input, output in pairs(sub.edges) do
+                input.pipe = {get_rate = function () return output.owner:get_rate() end}
+            end
+            for _, b in ipairs(sub.blocks) do b.in_gpu_subgraph = true end
+        end
+    end
+    function CompositeBlock:_initialize()
+        -- the original blocks first (members: their subclass initialize() designs the taps, the patched base initialize()
+        -- then skips the HOST handle), the substitutes afterwards: they take DEVICE handles from the initialised members
+        initialize(self)
+        for _, sub in ipairs(self._b200_substitutes or {}) do sub:initialize() end
     end
     function CompositeBlock:start(multiprocess)
         return start(self, false)       -- one process: the CUDA context cannot be forked (composite.lua:568-636)

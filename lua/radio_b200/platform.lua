@@ -53,6 +53,9 @@ function M.install(class, what, create, out_type)
     class.gpu_create = create
     class.gpu_what = what
     function class:initialize()
+        -- a member of a GPU sub-graph never runs its own process(): no HOST-pointer handle.  (A subclass's initialize() --
+        -- LowpassFilterBlock, SinglepoleLowpassFilterBlock ... -- has designed self.taps / b_taps by the time it calls this.)
+        if self.in_gpu_subgraph then return end
         self.handle = M.own(create(self, M.HOST), what)
         self.out = out_type(self).vector()
     end
@@ -83,6 +86,7 @@ function M.install_multi(class, what, create, out_types)
     class.gpu_create = create
     class.gpu_what = what
     function class:initialize()
+        if self.in_gpu_subgraph then return end
         self.handle = M.own(create(self, M.HOST), what)
         self.outs = {}
         for i, t in ipairs(out_types(self)) do self.outs[i] = t.vector() end

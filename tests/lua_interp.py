@@ -6,7 +6,7 @@ against mock `radio` / `ffi` / library objects instead of only being read.
 Covered: locals and upvalues (closures), assignment to names / fields / indices, multiple assignment and multiple returns,
 `...`, if / while / repeat / numeric and generic `for`, `break`, `return`, function and method definitions, method calls,
 table constructors, metatables (`__index` table or function, `__call`), arithmetic / comparison / logic / `..` / `#`,
-and the handful of standard functions the glue uses.  Not covered (not used by the glue): coroutines, `goto`,
+and the handful of standard functions the glue uses.  `goto` to a label of an enclosing block.  Not covered (not used by the glue or the reference core): coroutines,
 string methods via `:`, integer division, metamethods other than `__index` / `__call` / `__newindex`-less tables."""
 from lark import Token, Tree
 
@@ -45,6 +45,11 @@ def _key(k):
 
 class _Break(Exception):
     pass
+
+
+class _Goto(Exception):
+    def __init__(self, label):
+        self.label = label
 
 
 class _Return(Exception):
@@ -178,15 +183,72 @@ class Interp:
 
         import os as _os
         import math as _math
-        table = LuaTable({"insert": tinsert, "remove": tremove, "unpack": unpack, "concat": lambda t, sep="": [sep.join(self.tostring(x) for x in t.array())]})
-        string = LuaTable({"format": fmt, "len": lambda s: [len(s)], "sub": lambda s, i, j=-1: [s[int(i) - 1:(None if j == -1 else int(j))]]})
-        os_t = LuaTable({"getenv": lambda k: [_os.environ.get(k)]})
-        math_t = LuaTable({"floor": lambda x: [_math.floor(x)], "min": lambda *a: [min(a)], "max": lambda *a: [max(a)], "huge": float("inf")})
+        import re as _re
+
+        def lua_format(f, *a):
+            # Lua's %s applies tostring(); %d wants an integer-valued number
+            args, i = list(a), 0
+            out = []
+            for m in _re.finditer(r"%(?:%|[-+ #0]*\d*(?:\.\d+)?[a-zA-Z])|[^%]+", f):
+                tok = m.group(0)
+                if not tok.startswith("%") or tok == "%%":
+                    out.append("%" if tok == "%%" else tok)
+                    continue
+                v = args[i] if i < len(args) else None
+                i += 1
+                conv = tok[-1]
+                if conv == "s":
+                    out.append(tok % self.tostring(v))
+                elif conv in "di":
+                    out.append((tok[:-1] + "d") % int(v))
+                elif conv == "q":
+                    out.append('"%s"' % v)
+                else:
+                    out.append(tok % v)
+            return ["".join(out)]
+
+        def lua_gsub(s, pat, repl):
+            # plain-text patterns only (what the hot-path files use: "\n" -> ...)
+            if any(c in pat for c in "^$()%.[]*+-?"):
+                raise LuaError("string.gsub: pattern '%s' not supported by the test interpreter" % pat)
+            return [s.replace(pat, repl), s.count(pat)]
+
+        def lua_pcall(f, *a):
+            try:
+                return [True] + self.call(f, list(a))
+            except LuaError as e:
+                return [False, e.args[0]]
+
+        def lua_next(t, k=None):
+            keys = list(t.hash)
+            if k is None:
+                return [keys[0], t.hash[keys[0]]] if keys else [None]
+            i = keys.index(_key(k)) + 1
+            return [keys[i], t.hash[keys[i]]] if i < len(keys) else [None]
+
+        def rawset(t, k, v):
+            t.hash[_key(k)] = v
+            return [t]
+
+        table = LuaTable({"insert": tinsert, "remove": tremove, "unpack": unpack,
+                          "concat": lambda t, sep="", *a: [sep.join(self.tostring(x) for x in t.array())]})
+        string = LuaTable({"format": lua_format, "len": lambda s: [len(s)], "sub": lambda s, i, j=-1: [s[int(i) - 1:(None if j == -1 else int(j))]],
+                           "gsub": lua_gsub, "rep": lambda s, n, *a: [s * int(n)], "lower": lambda s: [s.lower()], "upper": lambda s: [s.upper()],
+                           "byte": lambda s, i=1: [ord(s[int(i) - 1])], "char": lambda *a: ["".join(chr(int(c)) for c in a)]})
+        os_t = LuaTable({"getenv": lambda k: [_os.environ.get(k)], "exit": lambda *a: lua_error("os.exit called"), "time": lambda *a: [0]})
+        mf = lambda f: (lambda *a: [f(*a)])
+        math_t = LuaTable({"floor": lambda x: [_math.floor(x)], "ceil": lambda x: [_math.ceil(x)], "min": lambda *a: [min(a)], "max": lambda *a: [max(a)],
+                           "huge": float("inf"), "pi": _math.pi, "sin": mf(_math.sin), "cos": mf(_math.cos), "tan": mf(_math.tan), "atan2": mf(_math.atan2),
+                           "atan": mf(_math.atan), "sqrt": mf(_math.sqrt), "abs": mf(abs), "exp": mf(_math.exp), "log": mf(_math.log),
+                           "log10": mf(_math.log10), "pow": mf(pow), "fmod": mf(_math.fmod), "sinh": mf(_math.sinh), "cosh": mf(_math.cosh)})
+        stream = lambda: LuaTable({"write": lambda self_, *a: [self_], "flush": lambda self_: []})
+        io_t = LuaTable({"stderr": stream(), "stdout": stream()})
         return {"pairs": lambda t: ["__pairs__", t], "ipairs": lambda t: ["__ipairs__", t], "error": lua_error, "assert": lua_assert,
                 "setmetatable": setmt, "getmetatable": lambda t: [t.meta if isinstance(t, LuaTable) else None], "tonumber": tonumber,
                 "tostring": lambda v=None: [self.tostring(v)], "type": lua_type, "unpack": unpack, "select": select, "print": lambda *a: [],
-                "table": table, "string": string, "os": os_t, "math": math_t, "require": lambda name: [self.require(name)],
-                "rawget": lambda t, k: [t.hash.get(_key(k))], "next": lambda t, k=None: [None]}
+                "table": table, "string": string, "os": os_t, "math": math_t, "io": io_t, "require": lambda name: [self.require(name)],
+                "rawget": lambda t, k: [t.hash.get(_key(k))], "rawset": rawset, "rawequal": lambda a, b: [a is b or a == b], "next": lua_next,
+                "pcall": lua_pcall}
 
     def tostring(self, v):
         if v is None:
@@ -276,9 +338,20 @@ class Interp:
     # ---- statements --------------------------------------------------------------------------------------------------
     def exec_block(self, block, scope):
         sc = Scope(scope)
-        for st in block.children:
+        stats = block.children
+        i = 0
+        while i < len(stats):
+            st = stats[i]
+            i += 1
             try:
                 self.exec_stat(st, sc)
+            except _Goto as g:
+                # `goto label` (LuaJIT): continue after the label if it is a statement of THIS block, else keep unwinding
+                # (the reference only jumps forward to a `::continue::` at the end of a loop body, composite.lua:194-210)
+                at = [k for k, s2 in enumerate(stats) if isinstance(s2, Tree) and s2.data == "label" and str(s2.children[0]) == g.label]
+                if not at:
+                    raise
+                i = at[0] + 1
             except LuaError as e:
                 if not getattr(e, "located", False) and isinstance(st, Tree) and getattr(st.meta, "line", None):
                     e.args = ("%s (line %d)" % (e.args[0], st.meta.line),)
@@ -399,8 +472,10 @@ class Interp:
             raise _Return(self.eval_list(st.children[0], sc) if st.children else [])
         elif d == "break_stat":
             raise _Break()
-        elif d == "stat":
+        elif d == "stat" or d == "label":
             return
+        elif d == "goto_stat":
+            raise _Goto(str(st.children[0]))
         else:
             raise LuaError("statement not supported by the test interpreter: %s" % d)
 

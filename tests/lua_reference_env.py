@@ -1,0 +1,136 @@
+"""The REAL reference core (radio/core/class.lua, util.lua, block.lua, composite.lua) and the REAL block files of the hot
+path, loaded from /root/reference into the test interpreter (tests/lua_interp.py), with mocks only for what needs LuaJIT's
+FFI or the OS: `ffi`, `radio.core.pipe`, `radio.core.debug`, `radio.core.platform`, `radio.types`, `radio.core.vector`.
+Used by tests/test_lua_reference.py to run the glue in lua/radio_b200/ against the reference's own class system and
+CompositeBlock:_prepare_to_run().  Nothing here is available on a machine without the reference tree (the tests skip)."""
+import os
+
+from tests.lua_interp import Interp, LuaTable
+
+REF = os.environ.get("LUARADIO_REFERENCE", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LUA = os.path.join(ROOT, "lua", "radio_b200")
+
+# reference class name -> module path (real files)
+REAL_BLOCKS = {
+    "FIRFilterBlock": "blocks/signal/firfilter", "LowpassFilterBlock": "blocks/signal/lowpassfilter",
+    "HighpassFilterBlock": "blocks/signal/highpassfilter", "BandpassFilterBlock": "blocks/signal/bandpassfilter",
+    "ComplexBandpassFilterBlock": "blocks/signal/complexbandpassfilter",
+    "FrequencyTranslatorBlock": "blocks/signal/frequencytranslator", "FrequencyDiscriminatorBlock": "blocks/signal/frequencydiscriminator",
+    "DownsamplerBlock": "blocks/signal/downsampler", "UpsamplerBlock": "blocks/signal/upsampler",
+    "IIRFilterBlock": "blocks/signal/iirfilter", "SinglepoleLowpassFilterBlock": "blocks/signal/singlepolelowpassfilter",
+    "SinglepoleHighpassFilterBlock": "blocks/signal/singlepolehighpassfilter", "FMDeemphasisFilterBlock": "blocks/signal/fmdeemphasisfilter",
+    "HilbertTransformBlock": "blocks/signal/hilberttransform", "ComplexMagnitudeBlock": "blocks/signal/complexmagnitude",
+    "ComplexToRealBlock": "blocks/signal/complextoreal", "MultiplyConstantBlock": "blocks/signal/multiplyconstant",
+    "MultiplyBlock": "blocks/signal/multiply", "MultiplyConjugateBlock": "blocks/signal/multiplyconjugate", "AddBlock": "blocks/signal/add",
+    "SubtractBlock": "blocks/signal/subtract", "DelayBlock": "blocks/signal/delay", "PLLBlock": "blocks/signal/pll",
+    "IQFileSource": "blocks/sources/iqfile", "RealFileSource": "blocks/sources/realfile", "IQFileSink": "blocks/sinks/iqfile",
+    "RealFileSink": "blocks/sinks/realfile",
+}
+REAL_COMPOSITES = {
+    "TunerBlock": "composites/tuner", "DecimatorBlock": "composites/decimator", "WBFMMonoDemodulator": "composites/wbfmmonodemodulator",
+    "WBFMStereoDemodulator": "composites/wbfmstereodemodulator", "AMSynchronousDemodulator": "composites/amsynchronousdemodulator",
+}
+REAL_UTILS = ["utilities/filter_utils", "utilities/window_utils", "utilities/format_utils", "utilities/spectrum_utils"]
+
+
+def available():
+    return os.path.isfile(os.path.join(REF, "radio", "core", "composite.lua"))
+
+
+def _read(rel):
+    with open(os.path.join(REF, "radio", rel + ".lua")) as f:
+        return f.read()
+
+
+def _glue(name):
+    with open(os.path.join(LUA, name + ".lua")) as f:
+        return f.read()
+
+
+def make_env(lib, cuda=True):
+    """Interpreter with the reference core + hot-path blocks + the glue registered as modules; `lib` is the mock library
+    platform.load() hands out.  Returns (interp, types)."""
+    vector_class = LuaTable({"name": "Vector"})
+
+    def make_type(name):
+        t = LuaTable({"type_name": name})
+
+        def vector(n=0):
+            v = LuaTable({"data": LuaTable(), "length": n or 0, "data_type": t, "_types": LuaTable({vector_class: True})})
+            for i in range(int(n or 0)):
+                v.hash["data"].hash[i] = LuaTable({"value": 0.0, "real": 0.0, "imag": 0.0})
+
+            def resize(self, m):
+                self.hash["length"] = m
+                return [self]
+            v.hash["resize"] = resize
+            return [v]
+
+        def vector_from_array(arr):
+            v = vector(arr.length())[0]
+            for i, x in enumerate(arr.array()):
+                v.hash["data"].hash[i] = x if isinstance(x, LuaTable) else LuaTable({"value": x})
+            return [v]
+        t.hash["vector"] = vector
+        t.hash["vector_from_array"] = vector_from_array
+        return t
+
+    types = LuaTable({k: make_type(k) for k in ("ComplexFloat32", "Float32", "Bit", "Byte")})
+    # ComplexFloat32(re, im) is called by a few blocks at module level / initialize
+    types.hash["ComplexFloat32"].meta = LuaTable({"__call": lambda self, re=0.0, im=0.0: [LuaTable({"real": re, "imag": im})]})
+    types.hash["Float32"].meta = LuaTable({"__call": lambda self, v=0.0: [LuaTable({"value": v})]})
+    ffi = LuaTable({
+        "cdef": lambda text: [], "typeof": lambda *a: [LuaTable()], "new": lambda ct, *a: [LuaTable({0: 0, "ctype": ct})],
+        "metatype": lambda ct, mt: [mt], "C": LuaTable(), "string": lambda s, *a: [s], "gc": lambda o, f: [o], "sizeof": lambda *a: [8],
+        "cast": lambda t, v: [v], "istype": lambda ct, v: [isinstance(v, LuaTable) and v.hash.get("ctype") is ct], "errno": lambda: [0],
+        "copy": lambda *a: [], "fill": lambda *a: [], "abi": lambda what: [what == "le"],
+    })
+
+    def new_pipe(cls, output, input_):
+        p = LuaTable({"output": output, "input": input_, "initialized": False})
+        p.hash["get_rate"] = lambda self: it.call(it.index(output.hash["owner"], "get_rate"), [output.hash["owner"]])
+
+        def initialize(self, *a):
+            self.hash["initialized"] = True
+            return []
+        p.hash["initialize"] = initialize
+        return [p]
+
+    def new_socket(cls):
+        return [LuaTable({"initialize": lambda self: []})]
+    pipe = LuaTable({"Pipe": LuaTable(), "ControlSocket": LuaTable(), "PipeMux": LuaTable()})
+    pipe.hash["Pipe"].meta = LuaTable({"__call": new_pipe})
+    pipe.hash["ControlSocket"].meta = LuaTable({"__call": new_socket})
+    debug = LuaTable({"print": lambda *a: [], "printf": lambda *a: [], "enabled": False})
+    platform = LuaTable({"features": LuaTable(), "libs": LuaTable(), "os": "Linux", "arch": "x64", "page_size": 4096,
+                         "load": lambda names: [cuda, lib if cuda else None], "alloc": lambda n: [LuaTable()]})
+    modules = {"ffi": ffi, "radio.core.pipe": pipe, "radio.core.debug": debug, "radio.core.platform": platform, "radio.types": types,
+               "radio.core.vector": LuaTable({"Vector": vector_class, "ObjectVector": LuaTable()}),
+               "radio.core.async": LuaTable({"callback": lambda *a: [None]})}
+    for rel in ("core/class", "core/util", "core/block", "core/composite"):
+        modules["radio." + rel.replace("/", ".")] = _read(rel)
+    for rel in list(REAL_BLOCKS.values()) + list(REAL_COMPOSITES.values()) + REAL_UTILS:
+        modules["radio." + rel.replace("/", ".")] = _read(rel)
+    for f in os.listdir(LUA):
+        if f.endswith(".lua"):
+            modules["radio_b200." + f[:-4]] = _glue(f[:-4])
+    # `radio` / `radio.blocks`: the registry the composites and user scripts see -- only the hot-path classes
+    lines = ["local radio = {}", "package_loaded_radio = radio",
+             "radio.CompositeBlock = require('radio.core.composite').CompositeBlock",
+             "radio.block = require('radio.core.block')", "radio.types = require('radio.types')"]
+    for name, rel in REAL_BLOCKS.items():
+        lines.append("radio.%s = require('radio.%s')" % (name, rel.replace("/", ".")))
+    lines.append("return radio")
+    modules["radio.blocks"] = "\n".join(lines)
+    comp = ["local radio = require('radio.blocks')"]
+    for name, rel in REAL_COMPOSITES.items():
+        comp.append("radio.%s = require('radio.%s')" % (name, rel.replace("/", ".")))
+    comp.append("return radio")
+    modules["radio"] = "\n".join(comp)
+    it = Interp(modules)
+    it.modules["string"] = it.G.vars["string"]
+    it.modules["math"] = it.G.vars["math"]
+    it.modules["io"] = it.G.vars["io"]
+    it.modules["os"] = it.G.vars["os"]
+    return it, types

@@ -1,0 +1,197 @@
+"""The glue in lua/radio_b200/ run against the REFERENCE'S OWN Lua code: radio/core/{class,util,block,composite}.lua and the
+real block / composite files of the hot path are loaded from the reference tree into the test interpreter
+(tests/lua_reference_env.py; mocks only for ffi, pipes, platform, types), the glue is installed the way INTEGRATION.md says
+(`require('radio_b200.blocks_patch')(radio)`), the flow graph of examples/rtlsdr_wbfm_mono.lua is built with the reference's
+CompositeBlock:connect, and CompositeBlock:_prepare_to_run() runs for real: differentiate, crawl, pipes, rate validation,
+initialize, evaluation order.  The mock library logs what the glue asked of libluaradio_b200.
+
+This is the closest the build image gets to running the glue under LuaJIT; it skips where the reference tree is absent."""
+import numpy as np
+import pytest
+
+from tests import lua_reference_env as E
+from tests.lua_interp import LuaError, LuaTable
+from tests.test_lua_exec import Handle, MockLib, read
+import os
+import re
+
+pytestmark = pytest.mark.skipif(not E.available(), reason="reference tree not present on this machine")
+
+MOCK_ENDS = """
+local block = require('radio.core.block')
+local types = require('radio.types')
+local Source = block.factory("MockSource")
+function Source:instantiate(rate, data_type)
+    self.rate = rate
+    self:add_type_signature({}, {block.Output("out", data_type or types.ComplexFloat32)})
+end
+function Source:get_rate() return self.rate end
+function Source:process() return nil end
+local Sink = block.factory("MockSink")
+function Sink:instantiate(data_type) self:add_type_signature({block.Input("in", data_type or types.Float32)}, {}) end
+function Sink:process(x) end
+return {Source = Source, Sink = Sink}
+"""
+
+
+def env(monkeypatch):
+    monkeypatch.delenv("LUARADIO_DISABLE_CUDA", raising=False)
+    monkeypatch.delenv("LUARADIO_CUDA_DEVICE", raising=False)
+    monkeypatch.delenv("LUARADIO_B200_SUPERCHUNK", raising=False)
+    from tests.lua_interp import Interp
+    cdef = Interp().run(read(os.path.join(E.LUA, "cdef.lua")))[0]
+    lib = MockLib(set(re.findall(r"\b(lrb200_\w+)\s*\(", cdef.hash["cdef"])))
+    it, types = E.make_env(lib)
+    it.modules["mock_ends"] = MOCK_ENDS
+    return it, lib, types
+
+
+def taps_of(vec):
+    return np.array([vec.hash[i].hash["value"] for i in range(len([k for k in vec.hash if isinstance(k, int)]))], np.float64)
+
+
+def test_reference_classes_load_and_the_glue_patches_them(monkeypatch):
+    it, lib, types = env(monkeypatch)
+    radio = it.require("radio")
+    for name in list(E.REAL_BLOCKS) + list(E.REAL_COMPOSITES) + ["CompositeBlock"]:
+        assert isinstance(radio.hash.get(name), LuaTable), name
+    it.call(it.require("radio_b200.blocks_patch"), [radio])
+    assert it.require("radio.core.platform").hash["features"].hash["cuda"] is True
+    b200 = it.require("radio_b200.platform")
+    # subclasses made by the reference's class.factory (which CACHES the parent's functions at creation) still reach the GPU
+    # form: new methods through the metatable chain, process functions through the explicit FIRFilterBlock.* / IIRFilterBlock.*
+    # lookups in instantiate()
+    for sub in ("LowpassFilterBlock", "HighpassFilterBlock", "BandpassFilterBlock", "ComplexBandpassFilterBlock"):
+        assert it.index(radio.hash[sub], "make_device_handle") is it.index(radio.hash["FIRFilterBlock"], "make_device_handle")
+    for sub in ("SinglepoleLowpassFilterBlock", "SinglepoleHighpassFilterBlock", "FMDeemphasisFilterBlock"):
+        assert it.index(radio.hash[sub], "make_device_handle") is it.index(radio.hash["IIRFilterBlock"], "make_device_handle")
+    lp = it.call(radio.hash["LowpassFilterBlock"], [128, 15e3])[0]
+    sigs = lp.hash["signatures"].array()
+    assert len(sigs) == 2 and all(s.hash["process_func"] is b200.hash["process"] for s in sigs)
+    de = it.call(radio.hash["FMDeemphasisFilterBlock"], [75e-6])[0]
+    assert all(s.hash["process_func"] is b200.hash["process"] for s in de.hash["signatures"].array())
+
+
+def test_wbfm_mono_example_through_the_reference_prepare_to_run(monkeypatch):
+    """examples/rtlsdr_wbfm_mono.lua:11-28 with a mock source and sink: after the reference's own _prepare_to_run() the seven
+    concrete blocks are ONE GPUChainBlock, initialised from taps the reference's initialize() methods designed at the rates
+    the rate links report."""
+    it, lib, types = env(monkeypatch)
+    top, conns, order, chain = it.run("""
+        local radio = require('radio')
+        require('radio_b200.blocks_patch')(radio)
+        local ends = require('mock_ends')
+        local source = ends.Source(1102500)
+        local tuner = radio.TunerBlock(-250e3, 200e3, 5)
+        local fm_demod = radio.FrequencyDiscriminatorBlock(1.25)
+        local af_filter = radio.LowpassFilterBlock(128, 15e3)
+        local af_deemphasis = radio.FMDeemphasisFilterBlock(75e-6)
+        local af_downsampler = radio.DownsamplerBlock(5)
+        local sink = ends.Sink()
+        local top = radio.CompositeBlock()
+        top:connect(source, tuner, fm_demod, af_filter, af_deemphasis, af_downsampler, sink)
+        local all_connections, evaluation_order = top:_prepare_to_run()
+        return top, all_connections, evaluation_order, top._b200_substitutes[1]
+    """)
+    names = [b.hash["name"] if "name" in b.hash else it.index(b, "name") for b in order.array()]
+    assert names == ["MockSource", "GPUChainBlock", "MockSink"]
+    assert len(conns.hash) == 2 and top.hash["_b200_substitutes"].length() == 1
+    members = [it.index(b, "name") for b in chain.hash["blocks"].array()]
+    assert members == ["FrequencyTranslatorBlock", "LowpassFilterBlock", "DownsamplerBlock", "FrequencyDiscriminatorBlock",
+                       "LowpassFilterBlock", "FMDeemphasisFilterBlock", "DownsamplerBlock"]
+    # every pipe of the collapsed graph was initialised by the reference, the chain reports the final rate
+    assert all(i.hash["pipe"].hash["initialized"] for i in conns.hash)
+    assert it.call(it.index(chain, "get_rate"), [chain]) == [1102500 / 25]
+    # library calls: the probe, then -- no HOST handle for any member -- the chain's graph
+    calls = [c[0] for c in lib.calls]
+    assert calls[:2] == ["lrb200_device_count", "lrb200_init"]
+    creates = ["lrb200_rotator_create", "lrb200_fir_create_crcf", "lrb200_downsample_create", "lrb200_discrim_create",
+               "lrb200_fir_create_rrrf", "lrb200_iir_create_rrrf", "lrb200_downsample_create"]
+    expect = ["lrb200_graph_create"]
+    for c in creates:
+        expect += [c, "lrb200_graph_append"]
+    assert calls[2:] == expect + ["lrb200_graph_commit"]
+    by_name = {}
+    for nm, args in lib.calls:
+        by_name.setdefault(nm, []).append(args)
+    assert all(a[-1] == 1 for nm in creates for a in by_name[nm])                   # DEVICE pointers
+    assert by_name["lrb200_rotator_create"][0][0] == pytest.approx(-250e3 / 1102500)
+    assert by_name["lrb200_discrim_create"][0][0] == pytest.approx(2 * np.pi * 1.25)       # gain = 2 pi modulation_index, as the header says
+    assert [a[:2] for a in by_name["lrb200_downsample_create"]] == [(5, 8), (5, 4)]
+    # the taps are the reference's own designs (filter_utils.lua run by the interpreter) at the right rates
+    from luaradio_b200.utilities import filter_utils as fu
+    t1 = taps_of(by_name["lrb200_fir_create_crcf"][0][0])
+    t2 = taps_of(by_name["lrb200_fir_create_rrrf"][0][0])
+    assert by_name["lrb200_fir_create_crcf"][0][1] == 128 and by_name["lrb200_fir_create_rrrf"][0][1] == 128
+    np.testing.assert_allclose(t1, np.asarray(fu.firwin_lowpass(128, 100e3 / (1102500 / 2)), np.float64), atol=1e-7)
+    np.testing.assert_allclose(t2, np.asarray(fu.firwin_lowpass(128, 15e3 / (220500 / 2)), np.float64), atol=1e-7)
+    b, n_b, a, n_a, _ = by_name["lrb200_iir_create_rrrf"][0]
+    from oracle import lr_oracle as O
+    ob, oa = O.fm_deemphasis_taps(75e-6, 220500.0)
+    assert (n_b, n_a) == (2, 2)
+    np.testing.assert_allclose(taps_of(b), ob, rtol=1e-6)
+    np.testing.assert_allclose(taps_of(a), oa, rtol=1e-6)
+    # process() of the chain is what the reference's run loop will call (bound by Block:differentiate)
+    patch = it.require("radio_b200.composite_patch")
+    assert chain.hash["process"] is patch.hash["GPUChainBlock"].hash["process"]
+    assert chain.hash["initialize"] is patch.hash["GPUChainBlock"].hash["initialize"]
+
+
+def test_composites_stereo_and_am_synchronous_through_the_reference(monkeypatch):
+    """The reference's own WBFMStereoDemodulator and AMSynchronousDemodulator composites: their concrete blocks become one
+    GPUDagBlock each, and the reference's rate validation and initialize pass over the members."""
+    it, lib, types = env(monkeypatch)
+    top, order = it.run("""
+        local radio = require('radio')
+        local types = require('radio.types')
+        require('radio_b200.blocks_patch')(radio)
+        local ends = require('mock_ends')
+        local top = radio.CompositeBlock()
+        local demod = radio.WBFMStereoDemodulator()
+        top:connect(ends.Source(220500), demod)
+        top:connect(demod, 'left', ends.Sink(), 'in')
+        top:connect(demod, 'right', ends.Sink(), 'in')
+        local all_connections, evaluation_order = top:_prepare_to_run()
+        return top, evaluation_order
+    """)
+    names = sorted(it.index(b, "name") for b in order.array())
+    assert names == ["GPUDagBlock", "MockSink", "MockSink", "MockSource"]
+    dag = top.hash["_b200_substitutes"].hash[1]
+    assert dag.hash["blocks"].length() == 14 and dag.hash["ext_out"].length() == 2
+    calls = [c[0] for c in lib.calls]
+    assert calls.count("lrb200_dag_create") == 1 and calls[-1] == "lrb200_dag_set_outputs"
+    assert calls.count("lrb200_pll_create") == 1 and calls.count("lrb200_binary_create") == 3 and calls.count("lrb200_delay_create") == 1
+    pll = [a for nm, a in lib.calls if nm == "lrb200_pll_create"][0]
+    assert pll == (100, 18950.0, 19050.0, 2, 220500, 1)          # wbfmstereodemodulator.lua: PLLBlock(100, 19e3-50, 19e3+50, 2) in Hz, the member's rate, DEVICE
+    # AM synchronous
+    it, lib, types = env(monkeypatch)
+    top, order = it.run("""
+        local radio = require('radio')
+        require('radio_b200.blocks_patch')(radio)
+        local ends = require('mock_ends')
+        local top = radio.CompositeBlock()
+        top:connect(ends.Source(1e6), radio.AMSynchronousDemodulator(100e3, 5e3), ends.Sink())
+        local all_connections, evaluation_order = top:_prepare_to_run()
+        return top, evaluation_order
+    """)
+    assert sorted(it.index(b, "name") for b in order.array()) == ["GPUDagBlock", "MockSink", "MockSource"]
+    assert [c[0] for c in lib.calls].count("lrb200_dag_add_graph") >= 1
+
+
+def test_without_the_cuda_feature_the_reference_runs_untouched(monkeypatch):
+    it, lib, types = env(monkeypatch)
+    monkeypatch.setenv("LUARADIO_DISABLE_CUDA", "1")
+    order = it.run("""
+        local radio = require('radio')
+        require('radio_b200.blocks_patch')(radio)
+        local ends = require('mock_ends')
+        local top = radio.CompositeBlock()
+        top:connect(ends.Source(1e6), radio.FrequencyTranslatorBlock(1e5), radio.DownsamplerBlock(2), ends.Sink(require('radio.types').ComplexFloat32))
+        top:_validate_inputs()
+        top:_differentiate()
+        local all_connections = top:_crawl_connections()
+        local n = 0
+        for _ in pairs(all_connections) do n = n + 1 end
+        return n
+    """)
+    assert order == [3] and lib.calls == []
