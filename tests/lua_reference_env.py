@@ -82,7 +82,8 @@ def make_env(lib, cuda=True):
     types.hash["Float32"].meta = LuaTable({"__call": lambda self, v=0.0: [LuaTable({"value": v})]})
     ffi = LuaTable({
         "cdef": lambda text: [], "typeof": lambda *a: [LuaTable()], "new": lambda ct, *a: [LuaTable({0: 0, "ctype": ct})],
-        "metatype": lambda ct, mt: [mt], "C": LuaTable(), "string": lambda s, *a: [s], "gc": lambda o, f: [o], "sizeof": lambda *a: [8],
+        "metatype": lambda ct, mt: [mt], "C": LuaTable({k: (lambda *a: [0]) for k in ("sigemptyset", "sigaddset", "sigprocmask", "signal", "sigpending",
+                                                                                  "sigismember", "getpid", "kill", "waitpid")}), "string": lambda s, *a: [s], "gc": lambda o, f: [o], "sizeof": lambda *a: [8],
         "cast": lambda t, v: [v], "istype": lambda ct, v: [isinstance(v, LuaTable) and v.hash.get("ctype") is ct], "errno": lambda: [0],
         "copy": lambda *a: [], "fill": lambda *a: [], "abi": lambda what: [what == "le"],
     })
@@ -95,13 +96,34 @@ def make_env(lib, cuda=True):
             self.hash["initialized"] = True
             return []
         p.hash["initialize"] = initialize
+        p.hash["write"] = lambda self, vec: self.hash.setdefault("queue", []).append(vec) or []
         return [p]
 
     def new_socket(cls):
         return [LuaTable({"initialize": lambda self: []})]
+
+    # PipeMux for the single-process run loop (block.lua:493-556): one vector per input per run_once(), EOF when an input
+    # queue is empty; write() appends to every downstream pipe's queue
+    def new_mux(cls, input_pipes, output_pipes, control_socket=None):
+        def read(self):
+            data = LuaTable()
+            for i, p in enumerate(input_pipes.array(), 1):
+                q = p.hash.setdefault("queue", [])
+                if not q:
+                    return [data, True, False]
+                data.hash[i] = q.pop(0)
+            return [data, False, False]
+
+        def write(self, data_out):
+            for i, pipes in enumerate(output_pipes.array(), 1):
+                for p in pipes.array():
+                    p.hash.setdefault("queue", []).append(data_out.hash[i])
+            return [False, None, False]
+        return [LuaTable({"read": read, "write": write})]
     pipe = LuaTable({"Pipe": LuaTable(), "ControlSocket": LuaTable(), "PipeMux": LuaTable()})
     pipe.hash["Pipe"].meta = LuaTable({"__call": new_pipe})
     pipe.hash["ControlSocket"].meta = LuaTable({"__call": new_socket})
+    pipe.hash["PipeMux"].meta = LuaTable({"__call": new_mux})
     debug = LuaTable({"print": lambda *a: [], "printf": lambda *a: [], "enabled": False})
     platform = LuaTable({"features": LuaTable(), "libs": LuaTable(), "os": "Linux", "arch": "x64", "page_size": 4096,
                          "load": lambda names: [cuda, lib if cuda else None], "alloc": lambda n: [LuaTable()]})

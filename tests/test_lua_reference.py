@@ -195,3 +195,48 @@ def test_without_the_cuda_feature_the_reference_runs_untouched(monkeypatch):
         return n
     """)
     assert order == [3] and lib.calls == []
+
+
+def test_reference_run_loop_drives_the_chain(monkeypatch):
+    """top:start() through the reference's own start() (forced single-process by the glue), _prepare_to_run() and the
+    round-robin run loop (composite.lua:647-707, Block:run_once block.lua:493-556) with mock pipes: every source vector is
+    one lrb200_graph_execute on the chain, the sink receives the chain's output vectors, and cleanup() flushes the chain."""
+    it, lib, types = env(monkeypatch)
+    top, sink, chain = it.run("""
+        local radio = require('radio')
+        require('radio_b200.blocks_patch')(radio)
+        local block = require('radio.core.block')
+        local types = require('radio.types')
+        local Source = block.factory("CountingSource")
+        function Source:instantiate(rate, vectors)
+            self.rate, self.left = rate, vectors
+            self:add_type_signature({}, {block.Output("out", types.ComplexFloat32)})
+        end
+        function Source:get_rate() return self.rate end
+        function Source:initialize() self.out = types.ComplexFloat32.vector(8192) end
+        function Source:process()
+            if self.left == 0 then return nil end
+            self.left = self.left - 1
+            return self.out
+        end
+        local Sink = block.factory("CountingSink")
+        function Sink:instantiate() self:add_type_signature({block.Input("in", types.Float32)}, {}) end
+        function Sink:initialize() self.vectors, self.samples = 0, 0 end
+        function Sink:process(x) self.vectors, self.samples = self.vectors + 1, self.samples + x.length end
+        local sink = Sink()
+        local top = radio.CompositeBlock()
+        top:connect(Source(1102500, 3), radio.TunerBlock(-250e3, 200e3, 5), radio.FrequencyDiscriminatorBlock(1.25),
+                    radio.LowpassFilterBlock(128, 15e3), radio.FMDeemphasisFilterBlock(75e-6), radio.DownsamplerBlock(5), sink)
+        top:start()            -- the user script says start() / run(): multiprocess by default in the reference
+        return top, sink, top._b200_substitutes[1]
+    """)
+    calls = [c[0] for c in lib.calls]
+    i0 = calls.index("lrb200_graph_commit") + 1
+    # three source vectors -> three executes; then the run loop ends on the source's EOF and cleanup() flushes the chain
+    assert calls[i0:] == ["lrb200_graph_max_output", "lrb200_graph_execute"] * 3 + ["lrb200_graph_max_output", "lrb200_graph_flush"]
+    ex = [a for nm, a in lib.calls if nm == "lrb200_graph_execute"]
+    assert all(a[0] is chain.hash["graph"] and a[2] == 8192 for a in ex)
+    # the flushed tail (the mock library reports 3 samples) was written to the chain's output pipe after the loop ended
+    assert sink.hash["vectors"] == 3 and sink.hash["samples"] == 3 * 8192
+    out_pipe = chain.hash["outputs"].hash[1].hash["pipes"].hash[1]
+    assert [v.hash["length"] for v in out_pipe.hash["queue"]] == [3]
