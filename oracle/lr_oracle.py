@@ -420,8 +420,11 @@ class Delay:
 
 class PLL:
     """pll.lua:113-170 restated operation by operation: Lua numbers are float64; the VCO output, the phase-detector
-    product (complexfloat32.lua:79-81) and the error (atan2f, :150-152) are float32 cells.  NOTE: the reference has no
-    pll_spec -- this block's parity is pinned only by this restatement (SURVEY.md 8c gaps)."""
+    product (complexfloat32.lua:79-81) and the error (atan2f, :150-152) are float32 cells.  The reference has no pll_spec;
+    this restatement is pinned instead against the reference's own pll.lua EXECUTED statement by statement in the test
+    interpreter on float32-faithful sample cells (tests/test_lua_reference.py::
+    test_pll_oracle_pinned_against_the_reference_pll_lua_executed: bit-identical over acquisition and lock, state carried
+    across calls)."""
 
     def __init__(self, loop_bandwidth, frequency_min, frequency_max, multiplier, rate):
         bw = 2 * math.pi * (loop_bandwidth / rate)

@@ -5,7 +5,7 @@ against mock `radio` / `ffi` / library objects instead of only being read.
 
 Covered: locals and upvalues (closures), assignment to names / fields / indices, multiple assignment and multiple returns,
 `...`, if / while / repeat / numeric and generic `for`, `break`, `return`, function and method definitions, method calls,
-table constructors, metatables (`__index` table or function, `__call`), arithmetic / comparison / logic / `..` / `#`,
+table constructors, metatables (`__index` table or function, `__newindex` function, `__call`, the arithmetic events), arithmetic / comparison / logic / `..` / `#`,
 and the handful of standard functions the glue uses.  `goto` to a label of an enclosing block.  Not covered (not used by the glue or the reference core): coroutines,
 string methods via `:`, integer division, metamethods other than `__index` / `__call` / `__newindex`-less tables."""
 from lark import Token, Tree
@@ -326,6 +326,9 @@ class Interp:
     def setindex(self, obj, key, value):
         if isinstance(obj, LuaTable):
             key = _key(key)
+            if key not in obj.hash and obj.meta is not None and obj.meta.hash.get("__newindex") is not None:
+                self.call(obj.meta.hash["__newindex"], [obj, key, value])
+                return
             if value is None:
                 obj.hash.pop(key, None)
             else:
@@ -627,6 +630,18 @@ class Interp:
                 op, b = str(kids[i]), self.eval(kids[i + 1], sc)
                 if a is None or b is None:
                     raise LuaError("attempt to perform arithmetic on a nil value")
+                if isinstance(a, LuaTable) or isinstance(b, LuaTable):          # arithmetic metamethods
+                    event = {"+": "__add", "-": "__sub", "*": "__mul", "/": "__div", "%": "__mod"}[op]
+                    h = None
+                    for operand in (a, b):
+                        if isinstance(operand, LuaTable) and operand.meta is not None and operand.meta.hash.get(event) is not None:
+                            h = operand.meta.hash[event]
+                            break
+                    if h is None:
+                        raise LuaError("attempt to perform arithmetic on a table value")
+                    a = (self.call(h, [a, b]) or [None])[0]
+                    i += 2
+                    continue
                 a = {"+": lambda x, y: x + y, "-": lambda x, y: x - y, "*": lambda x, y: x * y, "/": lambda x, y: x / y,
                      "%": lambda x, y: x - (x // y) * y}[op](a, b)
                 i += 2
@@ -637,6 +652,11 @@ class Interp:
                 return not self.truthy(v)
             if op == "#":
                 return v.length() if isinstance(v, LuaTable) else len(v)
+            if isinstance(v, LuaTable):
+                h = v.meta.hash.get("__unm") if v.meta is not None else None
+                if h is None:
+                    raise LuaError("attempt to perform arithmetic on a table value")
+                return (self.call(h, [v, v]) or [None])[0]
             return -v
         if d == "pow_exp":
             return self.eval(e.children[0], sc) ** self.eval(e.children[1], sc)

@@ -151,8 +151,132 @@ def make_env(lib, cuda=True):
     comp.append("return radio")
     modules["radio"] = "\n".join(comp)
     it = Interp(modules)
+    it.f32 = Float32Types(it, types, vector_class)
     it.modules["string"] = it.G.vars["string"]
     it.modules["math"] = it.G.vars["math"]
     it.modules["io"] = it.G.vars["io"]
     it.modules["os"] = it.G.vars["os"]
     return it, types
+
+
+class Float32Types:
+    """Float32-faithful stand-ins for the reference's cdata sample types, for RUNNING the reference's pure-Lua process() loops
+    in the interpreter: complex_float32_t {float real, imag} and float32_t {float value} are cells that round to float32 on
+    every store (radio/types/complexfloat32.lua:19-24, float32.lua:17-21); ComplexFloat32's operators and methods follow
+    complexfloat32.lua (products and sums are computed on Lua numbers = doubles and rounded when the result is constructed;
+    arg() is atan2f, abs() sqrtf).  Vectors made by make_vector() create their cells on first access."""
+
+    def __init__(self, it, types, vector_class):
+        import numpy as np
+        self.np, self.it, self.types, self.vector_class = np, it, types, vector_class
+        f32 = lambda v: float(np.float32(v))
+        self.f32 = f32
+
+        def cell_meta(fields):
+            store = {}
+
+            def index(t, k):
+                return [store.get((id(t), k), 0.0 if k in fields else None)]
+
+            def newindex(t, k, v):
+                store[(id(t), k)] = f32(v) if k in fields else v
+                return []
+            return index, newindex, store
+        # ---- ComplexFloat32
+        cidx, cnew, cstore = cell_meta(("real", "imag"))
+        self._cstore = cstore
+        methods = {}
+
+        def cindex(t, k):
+            if k in methods:
+                return [methods[k]]
+            return cidx(t, k)
+        self.cmeta = LuaTable({"__index": cindex, "__newindex": cnew})
+
+        def cnew_value(re=0.0, im=0.0):
+            t = LuaTable()
+            t.meta = self.cmeta
+            cstore[(id(t), "real")] = f32(re)
+            cstore[(id(t), "imag")] = f32(im)
+            self._keep.append(t)
+            return t
+        self._keep = []
+        self.complex = cnew_value
+        re = lambda t: cstore[(id(t), "real")]
+        im = lambda t: cstore[(id(t), "imag")]
+        self.re, self.im = re, im
+        self.cmeta.hash["__mul"] = lambda a, b: [cnew_value(re(a) * re(b) - im(a) * im(b), re(a) * im(b) + im(a) * re(b))]
+        self.cmeta.hash["__add"] = lambda a, b: [cnew_value(re(a) + re(b), im(a) + im(b))]
+        self.cmeta.hash["__sub"] = lambda a, b: [cnew_value(re(a) - re(b), im(a) - im(b))]
+        methods["conj"] = lambda a: [cnew_value(re(a), -im(a))]
+        methods["arg"] = lambda a: [float(np.arctan2(np.float32(im(a)), np.float32(re(a)), dtype=np.float32))]
+        methods["abs"] = lambda a: [float(np.sqrt(np.float32(re(a) * re(a) + im(a) * im(a)), dtype=np.float32))]
+        methods["abs_squared"] = lambda a: [re(a) * re(a) + im(a) * im(a)]
+        methods["scalar_mul"] = lambda a, k: [cnew_value(re(a) * k, im(a) * k)]
+        # ---- Float32
+        fidx, fnew, fstore = cell_meta(("value",))
+        self._fstore = fstore
+        self.fmeta = LuaTable({"__index": fidx, "__newindex": fnew})
+
+        def fnew_value(v=0.0):
+            t = LuaTable()
+            t.meta = self.fmeta
+            fstore[(id(t), "value")] = f32(v)
+            self._keep.append(t)
+            return t
+        self.real = fnew_value
+        C, F = types.hash["ComplexFloat32"], types.hash["Float32"]
+        C.meta = LuaTable({"__call": lambda self_, r=0.0, i=0.0: [cnew_value(r, i)]})
+        F.meta = LuaTable({"__call": lambda self_, v=0.0: [fnew_value(v)]})
+        C.hash["vector"] = lambda n=0: [self.make_vector(C, n)]
+        F.hash["vector"] = lambda n=0: [self.make_vector(F, n)]
+
+        def from_array(data_type):
+            def f(arr):
+                v = self.make_vector(data_type, arr.length())
+                for i, x in enumerate(arr.array()):
+                    v.hash["data"].hash[i] = (x if isinstance(x, LuaTable) else (cnew_value(x, 0.0) if data_type is C else fnew_value(x)))
+                return [v]
+            return f
+        C.hash["vector_from_array"] = from_array(C)
+        F.hash["vector_from_array"] = from_array(F)
+
+    def make_vector(self, data_type, n=0):
+        is_c = data_type is self.types.hash["ComplexFloat32"]
+        data = LuaTable()
+
+        def create(t, k):
+            cell = self.complex() if is_c else self.real()
+            t.hash[k] = cell
+            return [cell]
+
+        def assign(t, k, v):                       # out.data[i] = <value>: a struct copy in LuaJIT
+            if is_c:
+                t.hash[k] = self.complex(self.re(v), self.im(v))
+            else:
+                t.hash[k] = self.real(v if not isinstance(v, LuaTable) else self._fstore[(id(v), "value")])
+            return []
+        data.meta = LuaTable({"__index": create, "__newindex": assign})
+        v = LuaTable({"data": data, "length": int(n or 0), "data_type": data_type, "_types": LuaTable({self.vector_class: True})})
+
+        def resize(self_, m):
+            self_.hash["length"] = int(m)
+            return [self_]
+        v.hash["resize"] = resize
+        return v
+
+    def vector_from_numpy(self, x):
+        np = self.np
+        is_c = np.iscomplexobj(x)
+        v = self.make_vector(self.types.hash["ComplexFloat32" if is_c else "Float32"], len(x))
+        for i, s in enumerate(x):
+            v.hash["data"].hash[i] = self.complex(s.real, s.imag) if is_c else self.real(float(s))
+        return v
+
+    def to_numpy(self, v):
+        np = self.np
+        n = v.hash["length"]
+        d = v.hash["data"].hash
+        if v.hash["data_type"] is self.types.hash["ComplexFloat32"]:
+            return np.array([complex(self.re(d[i]), self.im(d[i])) for i in range(n)], np.complex64)
+        return np.array([self._fstore[(id(d[i]), "value")] for i in range(n)], np.float32)

@@ -46,8 +46,9 @@ def env(monkeypatch):
     return it, lib, types
 
 
-def taps_of(vec):
-    return np.array([vec.hash[i].hash["value"] for i in range(len([k for k in vec.hash if isinstance(k, int)]))], np.float64)
+def taps_of(it, data, n):
+    """float32 cells of a Float32 vector's data (tests/lua_reference_env.py: Float32Types)"""
+    return np.array([it.f32._fstore[(id(data.hash[i]), "value")] for i in range(n)], np.float64)
 
 
 def test_reference_classes_load_and_the_glue_patches_them(monkeypatch):
@@ -120,8 +121,8 @@ def test_wbfm_mono_example_through_the_reference_prepare_to_run(monkeypatch):
     assert [a[:2] for a in by_name["lrb200_downsample_create"]] == [(5, 8), (5, 4)]
     # the taps are the reference's own designs (filter_utils.lua run by the interpreter) at the right rates
     from luaradio_b200.utilities import filter_utils as fu
-    t1 = taps_of(by_name["lrb200_fir_create_crcf"][0][0])
-    t2 = taps_of(by_name["lrb200_fir_create_rrrf"][0][0])
+    t1 = taps_of(it, by_name["lrb200_fir_create_crcf"][0][0], 128)
+    t2 = taps_of(it, by_name["lrb200_fir_create_rrrf"][0][0], 128)
     assert by_name["lrb200_fir_create_crcf"][0][1] == 128 and by_name["lrb200_fir_create_rrrf"][0][1] == 128
     np.testing.assert_allclose(t1, np.asarray(fu.firwin_lowpass(128, 100e3 / (1102500 / 2)), np.float64), atol=1e-7)
     np.testing.assert_allclose(t2, np.asarray(fu.firwin_lowpass(128, 15e3 / (220500 / 2)), np.float64), atol=1e-7)
@@ -129,8 +130,8 @@ def test_wbfm_mono_example_through_the_reference_prepare_to_run(monkeypatch):
     from oracle import lr_oracle as O
     ob, oa = O.fm_deemphasis_taps(75e-6, 220500.0)
     assert (n_b, n_a) == (2, 2)
-    np.testing.assert_allclose(taps_of(b), ob, rtol=1e-6)
-    np.testing.assert_allclose(taps_of(a), oa, rtol=1e-6)
+    np.testing.assert_allclose(taps_of(it, b, 2), ob, rtol=1e-6)
+    np.testing.assert_allclose(taps_of(it, a, 2), oa, rtol=1e-6)
     # process() of the chain is what the reference's run loop will call (bound by Block:differentiate)
     patch = it.require("radio_b200.composite_patch")
     assert chain.hash["process"] is patch.hash["GPUChainBlock"].hash["process"]
@@ -240,3 +241,38 @@ def test_reference_run_loop_drives_the_chain(monkeypatch):
     assert sink.hash["vectors"] == 3 and sink.hash["samples"] == 3 * 8192
     out_pipe = chain.hash["outputs"].hash[1].hash["pipes"].hash[1]
     assert [v.hash["length"] for v in out_pipe.hash["queue"]] == [3]
+
+
+def test_pll_oracle_pinned_against_the_reference_pll_lua_executed(monkeypatch):
+    """The reference ships no pll_spec, so the oracle's PLL used to be an unpinned restatement.  Here the reference's OWN
+    radio/blocks/signal/pll.lua (instantiate, initialize, the process() loop: VCO, phase detector, loop filter, clamp, wrap)
+    is executed statement by statement in the interpreter on float32-faithful sample cells (tests/lua_reference_env.py:
+    Float32Types) and compared with oracle/lr_oracle.py: PLL on a 19 kHz pilot in noise, in two calls (state carried),
+    through acquisition and lock."""
+    from oracle import lr_oracle as O
+    it, lib, types = env(monkeypatch)
+    monkeypatch.setenv("LUARADIO_DISABLE_CUDA", "1")           # the stock reference block, no glue
+    rate, n = 220500.0, 2400
+    rng = np.random.default_rng(7)
+    t = np.arange(2 * n)
+    x = (0.8 * np.exp(2j * np.pi * 19011.0 / rate * t + 0.4j) + 0.05 * (rng.standard_normal(2 * n) + 1j * rng.standard_normal(2 * n))).astype(np.complex64)
+    blk = it.run("""
+        local PLLBlock = require('radio.blocks.signal.pll')
+        local types = require('radio.types')
+        local blk = PLLBlock(100, 18950, 19050, 2)
+        blk:differentiate({types.ComplexFloat32})
+        blk.inputs[1].pipe = {get_rate = function () return 220500 end}
+        blk:initialize()
+        return blk
+    """)[0]
+    ref = O.PLL(100, 18950, 19050, 2, rate)
+    for part in (x[:n], x[n:]):
+        out, err = it.call(it.index(blk, "process"), [blk, it.f32.vector_from_numpy(part)])
+        got_out, got_err = it.f32.to_numpy(out), it.f32.to_numpy(err)
+        exp_out, exp_err = ref.process(part)
+        assert np.max(np.abs(got_err - exp_err)) <= 1e-7 and np.max(np.abs(got_out - exp_out)) <= 1e-7
+        assert np.array_equal(got_err, exp_err) and np.array_equal(got_out, exp_out)          # the same float32 cells, bit for bit
+    # the loop did something: it pulled in from the band centre (19 000 Hz) towards the 19 011 Hz pilot and the error settled
+    assert abs(float(np.mean(exp_err[-400:]))) < 0.05 and np.std(exp_err[:200]) > np.std(exp_err[-200:]) * 0.5
+    f_locked = blk.hash["freq_locked"] * rate / (2 * np.pi)
+    assert 19000.5 < f_locked < 19030 and f_locked == pytest.approx(ref.freq * rate / (2 * np.pi), abs=1e-9)
