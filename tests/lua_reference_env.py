@@ -152,6 +152,9 @@ def make_env(lib, cuda=True):
     modules["radio"] = "\n".join(comp)
     it = Interp(modules)
     it.f32 = Float32Types(it, types, vector_class)
+    ffi.hash["sizeof"] = it.f32.sizeof
+    ffi.hash["copy"] = lambda dst, src, n=None: it.f32.memmove(dst, src, n) and []
+    ffi.hash["C"].hash["memmove"] = it.f32.memmove
     it.modules["string"] = it.G.vars["string"]
     it.modules["math"] = it.G.vars["math"]
     it.modules["io"] = it.G.vars["io"]
@@ -201,6 +204,7 @@ class Float32Types:
             self._keep.append(t)
             return t
         self._keep = []
+        self._where, self._elem_size, self._is_complex, self._cells = {}, {}, {}, {}     # cell -> (data table, index); data table -> element size / kind; (data table, index) -> cell
         self.complex = cnew_value
         re = lambda t: cstore[(id(t), "real")]
         im = lambda t: cstore[(id(t), "imag")]
@@ -213,6 +217,7 @@ class Float32Types:
         methods["abs"] = lambda a: [float(np.sqrt(np.float32(re(a) * re(a) + im(a) * im(a)), dtype=np.float32))]
         methods["abs_squared"] = lambda a: [re(a) * re(a) + im(a) * im(a)]
         methods["scalar_mul"] = lambda a, k: [cnew_value(re(a) * k, im(a) * k)]
+        methods["scalar_div"] = lambda a, k: [cnew_value(re(a) / k, im(a) / k)]
         # ---- Float32
         fidx, fnew, fstore = cell_meta(("value",))
         self._fstore = fstore
@@ -225,6 +230,11 @@ class Float32Types:
             self._keep.append(t)
             return t
         self.real = fnew_value
+        val = lambda t: fstore[(id(t), "value")]
+        self.fmeta.hash["__add"] = lambda a, b: [fnew_value(val(a) + val(b))]            # radio/types/float32.lua:51-85
+        self.fmeta.hash["__sub"] = lambda a, b: [fnew_value(val(a) - val(b))]
+        self.fmeta.hash["__mul"] = lambda a, b: [fnew_value(val(a) * val(b))]
+        self.fmeta.hash["__div"] = lambda a, b: [fnew_value(val(a) / val(b))]
         C, F = types.hash["ComplexFloat32"], types.hash["Float32"]
         C.meta = LuaTable({"__call": lambda self_, r=0.0, i=0.0: [cnew_value(r, i)]})
         F.meta = LuaTable({"__call": lambda self_, v=0.0: [fnew_value(v)]})
@@ -235,7 +245,7 @@ class Float32Types:
             def f(arr):
                 v = self.make_vector(data_type, arr.length())
                 for i, x in enumerate(arr.array()):
-                    v.hash["data"].hash[i] = (x if isinstance(x, LuaTable) else (cnew_value(x, 0.0) if data_type is C else fnew_value(x)))
+                    self.set_cell(v.hash["data"], i, x if isinstance(x, LuaTable) else (cnew_value(x, 0.0) if data_type is C else fnew_value(x)))
                 return [v]
             return f
         C.hash["vector_from_array"] = from_array(C)
@@ -243,19 +253,31 @@ class Float32Types:
 
     def make_vector(self, data_type, n=0):
         is_c = data_type is self.types.hash["ComplexFloat32"]
-        data = LuaTable()
+        data = LuaTable()                           # a PROXY: its own hash stays empty, so __index / __newindex always fire
+        cells = self._cells
 
         def create(t, k):
-            cell = self.complex() if is_c else self.real()
-            t.hash[k] = cell
+            cell = cells.get((id(t), k))
+            if cell is None:
+                cell = self.complex() if is_c else self.real()
+                cells[(id(t), k)] = cell
+                self._where[id(cell)] = (t, k)
             return [cell]
 
-        def assign(t, k, v):                       # out.data[i] = <value>: a struct copy in LuaJIT
+        def assign(t, k, v):                       # out.data[i] = <value>: a struct copy in LuaJIT, every time
             if is_c:
-                t.hash[k] = self.complex(self.re(v), self.im(v))
+                if v.meta is self.cmeta:
+                    cell = self.complex(self.re(v), self.im(v))
+                else:                              # a {re, im} pair (vector_from_array of filter_utils' complex taps)
+                    cell = self.complex(v.hash.get(1, v.hash.get("real", 0.0)), v.hash.get(2, v.hash.get("imag", 0.0)))
             else:
-                t.hash[k] = self.real(v if not isinstance(v, LuaTable) else self._fstore[(id(v), "value")])
+                cell = self.real(v if not isinstance(v, LuaTable) else self._fstore[(id(v), "value")])
+            cells[(id(t), k)] = cell
+            self._where[id(cell)] = (t, k)
             return []
+        self._elem_size[id(data)] = 8 if is_c else 4
+        self._is_complex[id(data)] = is_c
+        self._keep.append(data)
         data.meta = LuaTable({"__index": create, "__newindex": assign})
         v = LuaTable({"data": data, "length": int(n or 0), "data_type": data_type, "_types": LuaTable({self.vector_class: True})})
 
@@ -265,18 +287,61 @@ class Float32Types:
         v.hash["resize"] = resize
         return v
 
+    def set_cell(self, data, k, value):
+        self.it.call(data.meta.hash["__newindex"], [data, k, value])
+
+    def get_cell(self, data, k):
+        return self.it.call(data.meta.hash["__index"], [data, k])[0]
+
     def vector_from_numpy(self, x):
         np = self.np
         is_c = np.iscomplexobj(x)
         v = self.make_vector(self.types.hash["ComplexFloat32" if is_c else "Float32"], len(x))
         for i, s in enumerate(x):
-            v.hash["data"].hash[i] = self.complex(s.real, s.imag) if is_c else self.real(float(s))
+            self.set_cell(v.hash["data"], i, self.complex(s.real, s.imag) if is_c else self.real(float(s)))
         return v
 
     def to_numpy(self, v):
         np = self.np
         n = v.hash["length"]
-        d = v.hash["data"].hash
+        d = v.hash["data"]
         if v.hash["data_type"] is self.types.hash["ComplexFloat32"]:
-            return np.array([complex(self.re(d[i]), self.im(d[i])) for i in range(n)], np.complex64)
-        return np.array([self._fstore[(id(d[i]), "value")] for i in range(n)], np.float32)
+            return np.array([complex(self.re(self.get_cell(d, i)), self.im(self.get_cell(d, i))) for i in range(n)], np.complex64)
+        return np.array([self._fstore[(id(self.get_cell(d, i)), "value")] for i in range(n)], np.float32)
+
+    # ---- pointer emulation for the reference's pure-Lua branches: `v.data` is element 0, `v.data[k]` passed to memmove /
+    # ffi.copy is the address of element k (LuaJIT passes a struct reference where a pointer is expected)
+    def _locate(self, p):
+        if id(p) in self._elem_size:
+            return p, 0
+        if id(p) in self._where:
+            return self._where[id(p)]
+        from tests.lua_interp import LuaError
+        raise LuaError("memmove / ffi.copy: not a vector position")
+
+    def sizeof(self, p, *a):
+        if isinstance(p, LuaTable):
+            if p.meta is self.cmeta:
+                return [8]
+            if p.meta is self.fmeta:
+                return [4]
+        return [8]
+
+    def memmove(self, dst, src, nbytes):
+        (dt, di), (st, si) = self._locate(dst), self._locate(src)
+        size = self._elem_size[id(st)]
+        assert self._elem_size[id(dt)] == size and nbytes % size == 0
+        n = int(nbytes // size)
+        is_c = self._is_complex[id(st)]
+        vals = []
+        for k in range(n):
+            cell = self._cells.get((id(st), si + k))
+            if cell is None:
+                vals.append((0.0, 0.0) if is_c else 0.0)
+            else:
+                vals.append((self.re(cell), self.im(cell)) if is_c else self._fstore[(id(cell), "value")])
+        for k, v in enumerate(vals):
+            cell = self.complex(*v) if is_c else self.real(v)
+            self._cells[(id(dt), di + k)] = cell
+            self._where[id(cell)] = (dt, di + k)
+        return [dst]
