@@ -4,6 +4,8 @@ ragged chunking (streaming state), decimation phases, large sample indices, the 
 Tolerance (north_star: float32 match within 1e-5 relative): |got - ref| <= 1e-5 * max(1, ||ref||_inf)."""
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 
@@ -443,3 +445,15 @@ def test_interpolator_and_rational_resampler_stream(L, D, M, cplx):
 def test_resampler_remaining_instantiations(L, D, M, cplx):
     test_interpolator_and_rational_resampler_stream(L, D, M, cplx)
 
+
+# Added after the round's GPU budget was spent (hence the non-strict xfail: it has not run on a GPU yet): the CUDA chain
+# against what the stock REFERENCE computed for the whole chain (tests/golden/wbfm_chain_ref_executed.npz, made by executing
+# the reference's pure-Lua branches and run loop in the test interpreter).  The oracle reproduces that vector to 4.5e-8 on the
+# CPU (tests/test_oracle_golden.py), and the CUDA chain matches the oracle in test_wbfm_mono_chain above.
+@pytest.mark.xfail(strict=False, reason="not yet run on a GPU (added after the round's GPU budget ended)")
+@pytest.mark.parametrize("fuse", [True, False])
+@pytest.mark.parametrize("chunk", [1 << 22, 700])
+def test_wbfm_mono_chain_reference_executed_golden(fuse, chunk):
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wbfm_chain_ref_executed.npz"))
+    got, top = wbfm_graph(g["x"], rate=float(g["rate"]), fuse=fuse, chunk=chunk)
+    close(got, g["y"])

@@ -174,3 +174,24 @@ def test_oracle_file_sinks_round_trip_and_wav_header():
     assert list(O.file_sink_convert(np.array([-1.0, 1.0], np.float32), "s16le").view("<i2")) == [-32767, 32767]
     for (bits, ch), hexs in WAV_HEADERS.items():
         assert O.wav_header(256, ch, bits, 44100) == bytes.fromhex(hexs.replace(" ", "")), (bits, ch)
+
+
+def test_oracle_chain_against_the_reference_executed_golden():
+    """tests/golden/wbfm_chain_ref_executed.npz: the WHOLE rtlsdr_wbfm_mono chain as the stock reference computed it (its
+    pure-Lua process() branches and CompositeBlock run loop executed from the reference tree in the test interpreter,
+    tests/golden/make_chain_golden.py).  The oracle's chain -- whole and in the same ragged chunks -- must reproduce it at
+    the reference specs' own 1e-6."""
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, "wbfm_chain_ref_executed.npz"))
+    x, y, rate = g["x"], g["y"], float(g["rate"])
+    assert len(y) == len(x) // 25 and np.max(np.abs(y)) > 1e-3
+
+    def chain():
+        return O.Chain(O.tuner(-250e3, 200e3, 5, rate), O.FrequencyDiscriminator(1.25), O.lowpass_filter(128, 15e3, rate / 5, False),
+                       O.IIRFilter(*O.fm_deemphasis_taps(75e-6, rate / 5), False), O.Downsampler(5))
+    whole = chain().process(x)
+    assert np.max(np.abs(whole - y)) <= 1e-6
+    c = chain()
+    s = list(g["splits"])
+    parts = np.concatenate([c.process(x[a:b]) for a, b in zip(s[:-1], s[1:])])
+    assert np.max(np.abs(parts - y)) <= 1e-6
