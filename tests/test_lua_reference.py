@@ -10,10 +10,11 @@ import numpy as np
 import pytest
 
 from tests import lua_reference_env as E
-from tests.lua_interp import LuaError, LuaTable
-from tests.test_lua_exec import Handle, MockLib, read
 import os
 import re
+
+from tests.lua_interp import LuaTable
+from tests.test_lua_exec import MockLib, read
 
 pytestmark = pytest.mark.skipif(not E.available(), reason="reference tree not present on this machine")
 
