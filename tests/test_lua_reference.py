@@ -346,3 +346,50 @@ def test_oracle_chain_against_the_reference_chain_executed(monkeypatch):
     print("reference-executed chain vs oracle: max |diff| = %.3g over %d outputs" % (err, len(y)))
     assert err <= 1e-6 * scale, err                                      # measured: 4.5e-8 (float32 rounding of the accumulations)
     assert np.max(np.abs(ref)) > 1e-3                                    # a live signal came out of the filters' transient
+
+
+def test_top_spec_topology_through_the_reference_run_loop(monkeypatch):
+    """tests/top_spec.lua:14-55's shape: two sources into MultiplyConjugateBlock (two outside feeds: it stays a block of its
+    own, HOST-pointer handle, process(x, y) -> lrb200_block_execute_multi), then Lowpass -> FrequencyDiscriminator ->
+    DecimatorBlock as one chain; driven by the reference's own run loop."""
+    it, lib, types = env(monkeypatch)
+    top, sink = it.run("""
+        local radio = require('radio')
+        require('radio_b200.blocks_patch')(radio)
+        local block = require('radio.core.block')
+        local types = require('radio.types')
+        local Source = block.factory("CountingSource")
+        function Source:instantiate(rate, vectors)
+            self.rate, self.left = rate, vectors
+            self:add_type_signature({}, {block.Output("out", types.ComplexFloat32)})
+        end
+        function Source:get_rate() return self.rate end
+        function Source:initialize() self.out = types.ComplexFloat32.vector(4096) end
+        function Source:process()
+            if self.left == 0 then return nil end
+            self.left = self.left - 1
+            return self.out
+        end
+        local Sink = block.factory("CountingSink")
+        function Sink:instantiate() self:add_type_signature({block.Input("in", types.Float32)}, {}) end
+        function Sink:initialize() self.vectors = 0 end
+        function Sink:process(x) self.vectors = self.vectors + 1 end
+        local sink, mixer = Sink(), radio.MultiplyConjugateBlock()
+        local top = radio.CompositeBlock()
+        top:connect(Source(1e6, 2), 'out', mixer, 'in1')
+        top:connect(Source(1e6, 2), 'out', mixer, 'in2')
+        top:connect(mixer, radio.LowpassFilterBlock(16, 100e3), radio.FrequencyDiscriminatorBlock(5), radio.DecimatorBlock(25, {num_taps = 16}), sink)
+        top:start()
+        return top, sink
+    """)
+    subs = top.hash["_b200_substitutes"].array()
+    assert len(subs) == 1 and [it.index(b, "name") for b in subs[0].hash["blocks"].array()] == \
+        ["LowpassFilterBlock", "FrequencyDiscriminatorBlock", "LowpassFilterBlock", "DownsamplerBlock"]
+    calls = [c[0] for c in lib.calls]
+    assert calls.count("lrb200_binary_create") == 1
+    create = [a for nm, a in lib.calls if nm == "lrb200_binary_create"][0]
+    assert create == ("multiplyconjugate", 1, 0)                          # its own HOST-pointer handle
+    assert calls.count("lrb200_block_execute_multi") == 2 and calls.count("lrb200_graph_execute") == 2
+    em = [a for nm, a in lib.calls if nm == "lrb200_block_execute_multi"][0]
+    assert em[2] == 2 and em[3] == 4096 and em[5] == 1
+    assert calls[-2:] == ["lrb200_graph_max_output", "lrb200_graph_flush"] and sink.hash["vectors"] == 2
