@@ -181,3 +181,21 @@ def test_glue_has_no_undefined_or_accidental_globals():
         assert undefined_globals(open(os.path.join(LUA, f)).read()) == [], f
     # the analysis does see through to real problems
     assert undefined_globals("local a = 1\nlocal M = {}\n-- names in a comment: foo(bar)\nfunction M.f(x) return a + x - -typo end") == [("typo", 4)]
+
+
+def test_cdef_text_is_valid_c_in_declaration_order(tmp_path):
+    """LuaJIT's ffi.cdef is a C declaration parser: the generated text must be valid C as it stands (every typedef before its
+    first use), given only the two sample types radio.types declares.  gcc -fsyntax-only stands in for the FFI parser."""
+    import shutil
+    import pytest
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    from tests.lua_interp import Interp
+    cdef = Interp().run(open(os.path.join(LUA, "cdef.lua")).read())[0].hash["cdef"]
+    src = tmp_path / "cdef_check.c"
+    src.write_text("#include <stddef.h>\n#include <stdint.h>\n"
+                   "typedef struct { float real; float imag; } complex_float32_t;\n"      # radio/types/complexfloat32.lua:19-24
+                   "typedef struct { float value; } float32_t;\n"                         # radio/types/float32.lua:17-21
+                   + cdef + "\nint main(void) { return 0; }\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
