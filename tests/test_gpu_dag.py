@@ -228,7 +228,8 @@ def stereo_mpx(n, rate, rng):
 
 def test_wbfm_stereo_demodulator_dag():
     """composites/wbfmstereodemodulator.lua:22-64 at 220.5 kHz (the rate rtlsdr_wbfm_stereo.lua runs it at), against the
-    oracle wired block by block the same way.  PLL path unpinned (see test_pll_matches_the_restatement)."""
+    oracle wired block by block the same way (that wiring is pinned on the CPU against the reference's own composite executed in
+    the test interpreter: tests/test_oracle_golden.py::test_oracle_stereo_against_the_reference_executed_golden)."""
     rate, n = 220500.0, 150000
     rng = np.random.default_rng(9)
     x, left, right = stereo_mpx(n, rate, rng)

@@ -195,3 +195,28 @@ def test_oracle_chain_against_the_reference_executed_golden():
     s = list(g["splits"])
     parts = np.concatenate([c.process(x[a:b]) for a, b in zip(s[:-1], s[1:])])
     assert np.max(np.abs(parts - y)) <= 1e-6
+
+
+def test_oracle_stereo_against_the_reference_executed_golden():
+    """tests/golden/wbfm_stereo_ref_executed.npz: WBFMStereoDemodulator as the stock reference computed it (its composite,
+    the pure-Lua process() branches of its 14 blocks -- PLL included -- and its run loop executed from the reference tree in
+    the test interpreter, tests/golden/make_stereo_golden.py).  The oracle, wired block by block the same way
+    (wbfmstereodemodulator.lua:29-62), reproduces both channels through the PLL's acquisition and lock."""
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, "wbfm_stereo_ref_executed.npz"))
+    x, rate = g["x"], float(g["rate"])
+    fm = O.FrequencyDiscriminator(1.25).process(x)
+    hil = O.HilbertTransform(129).process(fm)
+    pilot = O.complex_bandpass_filter(129, [18e3, 20e3], rate).process(hil)
+    pll_out, _ = O.PLL(100, 19e3 - 50, 19e3 + 50, 2, rate).process(pilot)
+    dly = O.Delay(129).process(hil)
+    lpr = O.complex_to_real(O.lowpass_filter(128, 15e3, rate, True).process(dly))
+    lmr = O.complex_to_real(O.lowpass_filter(128, 15e3, rate, True).process(O.binary_op("multiplyconjugate", dly, pll_out)))
+    b, a = O.fm_deemphasis_taps(75e-6, rate)
+    left = O.IIRFilter(b, a, False).process(O.binary_op("add", lpr, lmr))
+    right = O.IIRFilter(b, a, False).process(O.binary_op("subtract", lpr, lmr))
+    assert len(left) == len(g["left"]) == len(x) and np.max(np.abs(left)) > 0.05
+    # measured 3e-8 (float32 accumulation in the reference's Lua loops against float64 here); the specs' own epsilon is 1e-6
+    assert np.max(np.abs(left - g["left"])) <= 1e-6 and np.max(np.abs(right - g["right"])) <= 1e-6
+    # the demodulator separated something: the two channels differ, as L (700 Hz) and R (2300 Hz) of the multiplex do
+    assert np.max(np.abs(g["left"][3000:] - g["right"][3000:])) > 0.02
