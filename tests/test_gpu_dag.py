@@ -3,7 +3,7 @@
   * two-input blocks (Multiply, MultiplyConjugate, Add, Subtract) and DelayBlock against the reference's golden vectors
     (whole and split calls) and on long streams against the oracle;
   * spectrum_utils.PSD against the reference's committed PSD vectors at the reference's tolerances;
-  * PLLBlock against the oracle's operation-by-operation restatement (the reference has no pll_spec: unpinned);
+  * PLLBlock against the oracle (the reference has no pll_spec; the oracle is pinned on the reference's pll.lua executed in the test interpreter);
   * the DAG scheduler: the reference's tests/top_spec.lua:14-55 topology (two sources -> MultiplyConjugate -> GPU run ->
     sink), a graph with a host-side CPU block in the middle, fan-out, the WBFM-stereo and AM-synchronous composites, and
     start()/status()/wait()/stop().
