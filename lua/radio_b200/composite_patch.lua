@@ -10,11 +10,12 @@
 --
 --   local top = radio.CompositeBlock(); top:connect(...); top:run()   -- unchanged user code
 --
--- install(radio) wraps four methods of CompositeBlock:
+-- install(radio) wraps five methods of CompositeBlock:
 --   _crawl_connections (composite.lua:343-381)  the top-level call returns the flat input-port -> output-port map;
 --                                               GPU sub-graphs are substituted there, before _connect_pipes (:383-393)
 --   _connect_pipes (composite.lua:383-393)      members of a sub-graph get a rate-only link in place of their pipe
 --   _initialize (composite.lua:416-424)         initialises the substitutes after the original blocks
+--   _prepare_to_run (composite.lua:426-466)     hands the global evaluation order to the substitutes (EOF flush)
 --   start (composite.lua:534-545)               forces multiprocess = false
 -- Set LUARADIO_B200_SUPERCHUNK=<samples> to pack the per-vector calls into pinned super-chunks
 -- (lrb200_graph_set_superchunk): throughput of the reference's 8192-sample vectors goes from launch-bound to
@@ -70,6 +71,24 @@ function GPUChainBlock:cleanup()
     out:resize(tonumber(n_out[0]))
     if out.length > 0 then
         for _, p in ipairs(self.outputs[1].pipes) do p:write(out) end
+        -- The run loop has already ended (the source's EOF stops it at once, composite.lua:662-681) and cleanup() runs in
+        -- evaluation order, so the blocks downstream are still alive: let each of them take one more turn on the flushed tail.
+        local downstream, todo = {}, {self}
+        while #todo > 0 do
+            local b = table.remove(todo)
+            for _, port in ipairs(b.outputs) do
+                for _, p in ipairs(port.pipes) do
+                    local consumer = p.input.owner
+                    if not downstream[consumer] then
+                        downstream[consumer] = true
+                        todo[#todo + 1] = consumer
+                    end
+                end
+            end
+        end
+        for _, b in ipairs(self.evaluation_order or {}) do
+            if downstream[b] then b:run_once() end
+        end
     end
 end
 
@@ -384,6 +403,12 @@ function M.install(radio)
         -- then skips the HOST handle), the substitutes afterwards: they take DEVICE handles from the initialised members
         initialize(self)
         for _, sub in ipairs(self._b200_substitutes or {}) do sub:initialize() end
+    end
+    local prepare = CompositeBlock._prepare_to_run
+    function CompositeBlock:_prepare_to_run()
+        local all_connections, evaluation_order = prepare(self)
+        for _, sub in ipairs(self._b200_substitutes or {}) do sub.evaluation_order = evaluation_order end
+        return all_connections, evaluation_order
     end
     function CompositeBlock:start(multiprocess)
         return start(self, false)       -- one process: the CUDA context cannot be forked (composite.lua:568-636)

@@ -475,12 +475,15 @@ def test_chain_block_lifecycle_against_the_library(monkeypatch):
     assert [c[0] for c in lib.calls] == ["lrb200_graph_max_output", "lrb200_graph_execute"]
     assert lib.calls[1][1][:4] == (graph, x.hash["data"], 8192, y.hash["data"]) and y is chain.hash["out"]
     # cleanup: the flushed samples go to every pipe of the output port
-    written = []
-    pipe = LuaTable({"write": lambda self, v: written.append(v.hash["length"]) or []})
+    written, turns = [], []
+    consumer = LuaTable({"outputs": LuaTable(), "run_once": lambda self: turns.append(1) or [True]})
+    pipe = LuaTable({"write": lambda self, v: written.append(v.hash["length"]) or [], "input": LuaTable({"owner": consumer})})
     chain.hash["outputs"].hash[1].hash["pipes"] = to_lua([pipe, pipe])
+    chain.hash["evaluation_order"] = to_lua([chain, consumer])
     lib.calls.clear()
     meth(chain, "cleanup")
     assert [c[0] for c in lib.calls] == ["lrb200_graph_max_output", "lrb200_graph_flush"] and written == [3, 3]
+    assert turns == [1]                                          # the block downstream takes one more turn on the flushed tail
     # the super-chunk switch
     monkeypatch.setenv("LUARADIO_B200_SUPERCHUNK", "1048576")
     lib.calls.clear()

@@ -19,6 +19,7 @@ from luaradio_b200 import _lib  # noqa: E402
 # radio/core/pipe.lua:495-615; radio/core/platform.lua:277-285)
 REFERENCE_METHODS = {
     "add_type_signature", "get_input_type", "get_output_type", "get_rate", "differentiate", "resize", "write", "vector",
+    "run_once",
 }
 
 
@@ -132,6 +133,9 @@ GLUE_RELIES_ON = [
     ("radio/blocks/signal/pll.lua", "self.loop_bw"), ("radio/blocks/signal/pll.lua", "self.freq_min"), ("radio/blocks/signal/pll.lua", "self.freq_max"),
     ("radio/blocks/signal/pll.lua", "self.multiplier"), ("radio/blocks/signal/pll.lua", "return out, err"),
     ("radio/core/block.lua", "self.outputs[i].data_type"), ("radio/core/block.lua", "self.inputs[i].data_type"),
+    ("radio/core/block.lua", "function Block:run_once"), ("radio/core/pipe.lua", "self.input = input"),
+    ("radio/core/composite.lua", "function CompositeBlock:_prepare_to_run"), ("radio/core/composite.lua", "function CompositeBlock:_initialize"),
+    ("radio/core/composite.lua", "return all_connections, evaluation_order"),
 ]
 
 

@@ -238,10 +238,11 @@ def test_reference_run_loop_drives_the_chain(monkeypatch):
     assert calls[i0:] == ["lrb200_graph_max_output", "lrb200_graph_execute"] * 3 + ["lrb200_graph_max_output", "lrb200_graph_flush"]
     ex = [a for nm, a in lib.calls if nm == "lrb200_graph_execute"]
     assert all(a[0] is chain.hash["graph"] and a[2] == 8192 for a in ex)
-    # the flushed tail (the mock library reports 3 samples) was written to the chain's output pipe after the loop ended
-    assert sink.hash["vectors"] == 3 and sink.hash["samples"] == 3 * 8192
+    # the flushed tail (the mock library reports 3 samples) was written to the chain's output pipe after the loop ended, and
+    # the sink downstream took one more turn on it before its own cleanup
+    assert sink.hash["vectors"] == 4 and sink.hash["samples"] == 3 * 8192 + 3
     out_pipe = chain.hash["outputs"].hash[1].hash["pipes"].hash[1]
-    assert [v.hash["length"] for v in out_pipe.hash["queue"]] == [3]
+    assert out_pipe.hash["queue"] == []
 
 
 def test_pll_oracle_pinned_against_the_reference_pll_lua_executed(monkeypatch):
@@ -392,4 +393,4 @@ def test_top_spec_topology_through_the_reference_run_loop(monkeypatch):
     assert calls.count("lrb200_block_execute_multi") == 2 and calls.count("lrb200_graph_execute") == 2
     em = [a for nm, a in lib.calls if nm == "lrb200_block_execute_multi"][0]
     assert em[2] == 2 and em[3] == 4096 and em[5] == 1
-    assert calls[-2:] == ["lrb200_graph_max_output", "lrb200_graph_flush"] and sink.hash["vectors"] == 2
+    assert calls[-2:] == ["lrb200_graph_max_output", "lrb200_graph_flush"] and sink.hash["vectors"] == 3      # two vectors + the flushed tail
