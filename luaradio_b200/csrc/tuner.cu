@@ -406,10 +406,13 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
             if (lane == 31) s_edge[warp] = acc[PT_R - 1];
             __syncthreads();                               // also fences the shared tile for the next iteration
             if (lane == 0 && warp > 0) left = s_edge[warp - 1];
+            bool zero_prev = false;                        // the carried sample is exactly (0, 0): stream start
             if (tid == 0 && tile == 0) {
                 // stream state: the previous call's last output (absolute phase) brought into this tile's frame
                 const float2 Pt = ROT ? phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B)) : make_float2(1.f, 0.f);
-                acc[0] = cmul(__ldg(prev_in), make_float2(Pt.x, -Pt.y));
+                const float2 pv = __ldg(prev_in);
+                acc[0] = cmul(pv, make_float2(Pt.x, -Pt.y));
+                if constexpr (EDGE) zero_prev = pv.x == 0.f && pv.y == 0.f;   // tile 0 reaches into the history: always an edge tile
             }
             // slots are tile-relative 32-bit indices: slot s holds y[m0 + s]; slots 1 .. lim-1 produce outputs
             const long long room = n_out - m0;             // > 1 for every launched tile
@@ -428,6 +431,19 @@ polyphase_crcf_kernel(const float2* __restrict__ x, const float2* __restrict__ h
                 const float2 ang = fast_atan2f_x2(make_float2(t0.y, t1.y), make_float2(t0.x, t1.x));
                 dout[r] = ang.x * inv_gain;
                 dout[r + 1] = ang.y * inv_gain;
+            }
+            if (EDGE && zero_prev) {
+                // y[0] * conj(0): the reference multiplies by prev_sample = ComplexFloat32() all the same
+                // (frequencydiscriminator.lua:72, complexfloat32.lua:79-81) and takes atan2f of a product of SIGNED zeros:
+                // real = yr*0 - yi*(-0) is -0 when yr and yi are both negative, and atan2f(+0, -0) = pi -- a click of
+                // pi / gain at the start of one stream in four.  The packed fast atan2 above works in the tile's rotated
+                // frame and tests x < 0, so this one sample is redone in the absolute frame with IEEE operations.
+                const float2 Pt = ROT ? phasor_from_fix(P.turns_fix * (P.g0 + (uint64_t)B)) : make_float2(1.f, 0.f);
+                const float2 ya = ROT ? cmul(acc[1], Pt) : acc[1];
+                const float pz = 0.f, nz = -0.f;
+                const float re = __fsub_rn(__fmul_rn(ya.x, pz), __fmul_rn(ya.y, nz));
+                const float im = __fadd_rn(__fmul_rn(ya.x, nz), __fmul_rn(ya.y, pz));
+                dout[1] = atan2f(im, re) * inv_gain;
             }
 #pragma unroll
             for (int r = 0; r < PT_R; ++r) {

@@ -448,12 +448,13 @@ def test_wbfm_mono_chain_reference_executed_golden(chunk):
     close(got, g["y"])
 
 
-# OPEN ITEM: the FUSED graph (tuner+discrim | fir*iir1+pole) failed this comparison in the one GPU run the
-# round had left for it, for both chunkings, while the unfused graph above passed and the fused graph passes every
-# long-stream test (test_wbfm_mono_chain: 600 000 samples incl. the stream start, chunk 1234; test_audio_tail_noble_identity
-# down to 73-sample calls; smoke: 200 000 samples at 7e-8).  The size of the deviation has not been measured yet -- the
-# assertion message below prints it -- so this stays a non-strict xfail instead of being dropped.
-@pytest.mark.xfail(strict=False, reason="fused graph deviates on a 1 650-sample stream (seen once on a GPU, magnitude unmeasured): open item")
+# The FUSED graph (tuner+discrim | fir*iir1+pole) failed this comparison in the round's last GPU run while the unfused graph
+# passed.  Cause, found afterwards on the CPU (an arithmetic emulation of the fused stage reproduces the 0.018 deviation): the
+# reference's FIRST discriminator output is atan2f of y[0] * conj(0), a product of SIGNED zeros -- pi / gain = 0.4 when
+# both parts of y[0] are negative (one stream in four; this vector is one), 0 otherwise -- and the fused epilogue's packed
+# fast atan2 returned 0.  tuner.cu now redoes that one sample with IEEE operations in the edge-tile kernel (the interior
+# kernel's SASS is unchanged).  The fix was made after the GPU budget reached zero: non-strict xfail until it has run once.
+@pytest.mark.xfail(strict=False, reason="stream-start signed-zero fix in the fused discriminator has not run on a GPU yet")
 @pytest.mark.parametrize("chunk", [1 << 22, 700])
 def test_wbfm_mono_chain_reference_executed_golden_fused(chunk):
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wbfm_chain_ref_executed.npz"))
