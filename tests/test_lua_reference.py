@@ -394,3 +394,33 @@ def test_top_spec_topology_through_the_reference_run_loop(monkeypatch):
     em = [a for nm, a in lib.calls if nm == "lrb200_block_execute_multi"][0]
     assert em[2] == 2 and em[3] == 4096 and em[5] == 1
     assert calls[-2:] == ["lrb200_graph_max_output", "lrb200_graph_flush"] and sink.hash["vectors"] == 3      # two vectors + the flushed tail
+
+
+def test_discriminator_first_sample_signed_zero_artefact(monkeypatch):
+    """frequencydiscriminator.lua:33,72: the first sample is multiplied by conj(ComplexFloat32()) and atan2f sees a product of
+    signed zeros -- pi / gain when both parts of the first sample are negative, 0 in the three other quadrants.  The
+    reference's own pure-Lua process() executed on float32-faithful cells, the oracle, and (on the GPU) both the stand-alone
+    and the fused discriminator must agree on it (tests/test_gpu_stream.py::test_wbfm_mono_chain_reference_executed_golden*)."""
+    from oracle import lr_oracle as O
+    monkeypatch.setenv("LUARADIO_DISABLE_CUDA", "1")
+    it, lib, types = env(monkeypatch)
+    monkeypatch.setenv("LUARADIO_DISABLE_CUDA", "1")
+    make = it.run("""
+        local Disc = require('radio.blocks.signal.frequencydiscriminator')
+        local types = require('radio.types')
+        return function ()
+            local blk = Disc(1.25)
+            blk:differentiate({types.ComplexFloat32})
+            blk:initialize()
+            return blk
+        end
+    """)[0]
+    gain = 2 * np.pi * 1.25
+    for re, im, first in ((0.3, 0.2, 0.0), (-0.3, 0.2, 0.0), (0.3, -0.2, 0.0), (-0.3, -0.2, np.pi / gain)):
+        x = np.array([complex(re, im), complex(0.1, 0.4), complex(-0.2, 0.1)], np.complex64)
+        blk = it.call(make, [])[0]
+        out = it.call(it.index(blk, "process"), [blk, it.f32.vector_from_numpy(x)])[0]
+        got = it.f32.to_numpy(out)
+        exp = O.FrequencyDiscriminator(1.25).process(x)
+        assert np.max(np.abs(got - exp)) <= 3e-8, (re, im, got, exp)          # one float32 ulp in the gain scaling
+        assert abs(float(got[0]) - first) <= 1e-7 and abs(float(exp[0]) - first) <= 1e-7, (re, im, got[0], exp[0])
