@@ -30,6 +30,9 @@ REAL_BLOCKS = {
 REAL_COMPOSITES = {
     "TunerBlock": "composites/tuner", "DecimatorBlock": "composites/decimator", "WBFMMonoDemodulator": "composites/wbfmmonodemodulator",
     "WBFMStereoDemodulator": "composites/wbfmstereodemodulator", "AMSynchronousDemodulator": "composites/amsynchronousdemodulator",
+    "NBFMDemodulator": "composites/nbfmdemodulator", "AMEnvelopeDemodulator": "composites/amenvelopedemodulator",
+    "SSBDemodulator": "composites/ssbdemodulator", "InterpolatorBlock": "composites/interpolator",
+    "RationalResamplerBlock": "composites/rationalresampler",
 }
 REAL_UTILS = ["utilities/filter_utils", "utilities/window_utils", "utilities/format_utils", "utilities/spectrum_utils"]
 

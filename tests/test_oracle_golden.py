@@ -220,3 +220,43 @@ def test_oracle_stereo_against_the_reference_executed_golden():
     assert np.max(np.abs(left - g["left"])) <= 1e-6 and np.max(np.abs(right - g["right"])) <= 1e-6
     # the demodulator separated something: the two channels differ, as L (700 Hz) and R (2300 Hz) of the multiplex do
     assert np.max(np.abs(g["left"][3000:] - g["right"][3000:])) > 0.02
+
+
+def _composite_oracles(rate):
+    """The oracle wired the way the reference's composites wire their blocks (composites/*.lua), by fixture name."""
+    def iir_hp(cutoff):
+        b, a = O.singlepole_highpass_taps(cutoff, rate)
+        return O.IIRFilter(b, a, False)
+
+    def am_sync(x):
+        f = O.complex_bandpass_filter(129, [10e3 - 5e3, 10e3 + 5e3], rate).process(x)         # amsynchronousdemodulator.lua:25-45
+        pll, _ = O.PLL(1000, 10e3 - 100, 10e3 + 100, 1.0, rate).process(f)
+        d = O.complex_to_real(O.binary_op("multiplyconjugate", f, pll))
+        return O.Chain(iir_hp(100), O.lowpass_filter(128, 5e3, rate, False)).process(d)
+    return {
+        "nbfm": O.Chain(O.lowpass_filter(128, 5e3 + 4e3, rate, True), O.FrequencyDiscriminator(5e3 / 4e3), O.lowpass_filter(128, 4e3, rate, False)).process,
+        "am_envelope": O.Chain(O.complex_magnitude, iir_hp(100), O.lowpass_filter(128, 5e3, rate, False)).process,
+        "ssb_usb": O.Chain(O.complex_bandpass_filter(129, [0, 3e3], rate), O.complex_to_real, O.lowpass_filter(128, 3e3, rate, False)).process,
+        "ssb_lsb": O.Chain(O.complex_bandpass_filter(129, [0, -3e3], rate), O.complex_to_real, O.lowpass_filter(128, 3e3, rate, False)).process,
+        "am_synchronous": am_sync,
+        "decimator_c": O.decimator(4, True, 64).process,
+        "interpolator_c": O.interpolator(3, True, 48).process,
+        "resampler_c": O.rational_resampler(3, 2, True, 48).process,
+        "interpolator_r": O.interpolator(2, False, 32).process,
+    }
+
+
+@pytest.mark.parametrize("name", ["nbfm", "am_envelope", "ssb_usb", "ssb_lsb", "am_synchronous", "decimator_c", "interpolator_c", "resampler_c",
+                                  "interpolator_r"])
+def test_oracle_composites_against_the_reference_executed_goldens(name):
+    """tests/golden/composites_ref_executed.npz: the reference's NBFM / AM-envelope / SSB / AM-synchronous demodulators and
+    its Decimator / Interpolator / RationalResampler composites as the stock reference computed them (composite wiring, the
+    pure-Lua process() branches and the run loop executed from the reference tree in the test interpreter,
+    tests/golden/make_composite_goldens.py).  The oracle wired the same way must reproduce them at the reference specs' 1e-6
+    (the resampler composites scale by L: 1e-6 relative to that)."""
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, "composites_ref_executed.npz"))
+    x, y, rate = g[name + "_x"], g[name + "_y"], float(g[name + "_rate"])
+    got = _composite_oracles(rate)[name](x)
+    assert len(got) == len(y) and np.max(np.abs(y)) > 1e-3
+    assert np.max(np.abs(got - y)) <= 1e-6 * max(1.0, float(np.max(np.abs(y)))), float(np.max(np.abs(got - y)))
