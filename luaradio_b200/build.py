@@ -15,8 +15,11 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libluaradio_b200.so")
 SOURCES = ["capi.cu", "graph.cu", "fir_direct.cu", "fir_fft.cu", "tuner.cu", "elementwise.cu", "iir.cu", "synth.cu", "iqconv.cu", "resample.cu", "aux_blocks.cu", "poly_generic.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-# --split-compile 0: the fully unrolled tuner / FFT kernels are dozens of large kernels per file; let ptxas use every core
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--split-compile", "0"]
+# --split-compile 0: the fully unrolled tuner / FFT kernels are dozens of large kernels per file; let ptxas use every core.
+# With it the generated SASS depends on thread scheduling (two variants per file were seen, profiles/README.md "Build
+# reproducibility note"); LRB200_DETERMINISTIC=1 compiles single-threaded instead: reproducible, ~3x the build time.
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+         "--split-compile", "1" if os.environ.get("LRB200_DETERMINISTIC") else "0"]
 FLAGS += os.environ.get("LRB200_NVCC_EXTRA", "").split()
 
 
