@@ -1,7 +1,9 @@
 """A Lua 5.1 grammar for lark (Earley), used to PARSE the LuaJIT glue in lua/radio_b200/ -- LuaJIT is not installed in the
 build image, so this is as close to `luajit -bl` as the CPU test-suite gets.  The grammar follows the reference manual's
 "complete syntax of Lua" (section 8 of the 5.1 manual) plus LuaJIT's `goto` / `::label::` (the reference uses them,
-radio/core/composite.lua:194); operator precedence is spelled out in layers."""
+radio/core/composite.lua:194); operator precedence is spelled out in layers.  The one ambiguity of the language -- `f\n(g)(x)`:
+a call continuation or a new statement that starts with a parenthesis -- is resolved the way Lua does (continuation) by giving
+the parenthesised prefix expression a negative priority."""
 from lark import Lark
 
 LUA_GRAMMAR = r"""
@@ -40,7 +42,8 @@ explist: exp ("," exp)*
 ?pow_exp: atom ("^" unary_exp)?
 ?atom: NIL | FALSE | TRUE | NUMBER | STRING | LONGSTRING | VARARG | function | prefixexp | tableconstructor
 
-?prefixexp: var | functioncall | "(" exp ")"
+?prefixexp: var | functioncall | paren_exp
+paren_exp.-10: "(" exp ")"
 var: NAME | prefixexp "[" exp "]" | prefixexp "." NAME
 functioncall: prefixexp args | prefixexp ":" NAME args
 args: "(" explist? ")" | tableconstructor | STRING | LONGSTRING

@@ -294,6 +294,8 @@ class Interp:
             return self.call(h, [f] + list(args))
         if f is None:
             raise LuaError("attempt to call a nil value")
+        if not callable(f):
+            raise LuaError("attempt to call a %s value" % type(f).__name__)
         r = f(*args)
         if r is None:
             return []
@@ -576,6 +578,8 @@ class Interp:
         if d == "functioncall":
             r = self.eval_call(e, sc)
             return r[0] if r else None
+        if d == "paren_exp":                          # (f()) keeps the first value only
+            return self.eval(e.children[0], sc)
         if d == "function":
             return LuaFunction(self, e.children[0], sc, False)
         if d == "tableconstructor":

@@ -140,6 +140,8 @@ def make_env(lib, cuda=True):
     for f in os.listdir(LUA):
         if f.endswith(".lua"):
             modules["radio_b200." + f[:-4]] = _glue(f[:-4])
+            if f == "init.lua":
+                modules["radio_b200"] = modules["radio_b200.init"]
     # `radio` / `radio.blocks`: the registry the composites and user scripts see -- only the hot-path classes
     lines = ["local radio = {}", "package_loaded_radio = radio",
              "radio.CompositeBlock = require('radio.core.composite').CompositeBlock",

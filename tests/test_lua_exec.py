@@ -119,6 +119,8 @@ def make_env(cuda=True):
     for f in os.listdir(LUA):
         if f.endswith(".lua"):
             modules["radio_b200." + f[:-4]] = read(os.path.join(LUA, f))
+            if f == "init.lua":
+                modules["radio_b200"] = modules["radio_b200.init"]
     it = Interp(modules)
     it.cdefs = cdefs
     return it, lib, types

@@ -424,3 +424,24 @@ def test_discriminator_first_sample_signed_zero_artefact(monkeypatch):
         exp = O.FrequencyDiscriminator(1.25).process(x)
         assert np.max(np.abs(got - exp)) <= 3e-8, (re, im, got, exp)          # one float32 ulp in the gain scaling
         assert abs(float(got[0]) - first) <= 1e-7 and abs(float(exp[0]) - first) <= 1e-7, (re, im, got[0], exp[0])
+
+
+def test_entry_point_module(monkeypatch):
+    """require('radio_b200')(radio): true with the backend active and the classes patched, false (and nothing touched) with the
+    kill switch."""
+    it, lib, types = env(monkeypatch)
+    active, has = it.run("""
+        local radio = require('radio')
+        local active = require('radio_b200')(radio)
+        return active, radio.DownsamplerBlock.make_device_handle ~= nil
+    """)
+    assert active is True and has is True
+    monkeypatch.setenv("LUARADIO_DISABLE_CUDA", "1")
+    it, lib, types = env(monkeypatch)
+    monkeypatch.setenv("LUARADIO_DISABLE_CUDA", "1")
+    active, has = it.run("""
+        local radio = require('radio')
+        local active = require('radio_b200')(radio)
+        return active, radio.DownsamplerBlock.make_device_handle ~= nil
+    """)
+    assert active is False and has is False and lib.calls == []
